@@ -1,0 +1,14 @@
+"""puffer_phc_b200 -- B200-native (sm_100a) implementation of puffer-phc's per-step rollout hot path.
+
+Drop-in modules mirror the reference's call surface:
+
+* ``puffer_phc_b200.motion_lib.MotionLibSMPL.get_motion_state``   (reference puffer_phc/motion_lib.py:549-626)
+* ``puffer_phc_b200.envs.common.compute_*``                        (reference puffer_phc/envs/common.py)
+* ``puffer_phc_b200.policies.running_norm.RunningNorm``            (reference puffer_phc/policies/running_norm.py)
+* ``puffer_phc_b200.c_gae.compute_gae``                            (reference puffer_phc/c_gae.pyx)
+* ``puffer_phc_b200.fused_step.FusedStep``                         (the whole post-physics step in one kernel)
+
+All arithmetic runs in hand-written CUDA kernels behind the C-ABI library ``libphc_b200.so``
+(include/phc_b200.h).  There is no CPU fallback: every entry point raises if the library is missing.
+"""
+__version__ = "0.1.0"

@@ -1,0 +1,55 @@
+import os
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+
+# north_star tolerance: 1e-5 relative (fp32) for states, observations, rewards and advantages, with a
+# small absolute floor because many observation entries are differences that sit near zero
+# (SURVEY.md section 8d "Parity tolerances").
+RTOL = 1e-5
+ATOL = 2e-6
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+
+
+def load_npz(name):
+    z = np.load(os.path.join(GOLDEN, name))
+    return {k: z[k] for k in z.files}
+
+
+def assert_close(a, b, rtol=RTOL, atol=ATOL, what=""):
+    """|a-b| <= rtol*|b| + atol elementwise, with a useful message (b is the reference)."""
+    a = np.asarray(a, dtype=np.float64)
+    b = np.asarray(b, dtype=np.float64)
+    assert a.shape == b.shape, f"{what}: shape {a.shape} vs {b.shape}"
+    bad = ~(np.abs(a - b) <= rtol * np.abs(b) + atol)
+    both_nan = np.isnan(a) & np.isnan(b)
+    bad &= ~both_nan
+    if bad.any():
+        idx = np.argwhere(bad)
+        err = np.abs(a - b)
+        worst = np.unravel_index(np.nanargmax(np.where(bad, err, 0)), a.shape)
+        raise AssertionError(
+            f"{what}: {bad.sum()} of {a.size} outside rtol={rtol} atol={atol}; worst at {worst}: "
+            f"got {a[worst]!r} want {b[worst]!r} (abs err {err[worst]:.3e}); first bad index {tuple(idx[0])}")
+
+
+def assert_equal(a, b, what=""):
+    a, b = np.asarray(a), np.asarray(b)
+    assert a.shape == b.shape, f"{what}: shape {a.shape} vs {b.shape}"
+    n = int((a != b).sum())
+    assert n == 0, f"{what}: {n} of {a.size} differ (first at {tuple(np.argwhere(a != b)[0])})"
+
+
+@pytest.fixture(scope="session")
+def golden():
+    return {n: load_npz(n + ".npz") for n in ("cmu_tables", "cmu_step", "synth_tables", "synth_step", "gae", "rms", "sample_time")}
