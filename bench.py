@@ -1,0 +1,324 @@
+#!/usr/bin/env python
+"""bench.py -- env-steps/s of the fused rollout-side step on B200, with roofline, CPU baseline and e2e legs.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--envs 65536] [--impl ours|reference]
+
+One "step" = one pass of the hot path over one batch of N synthetic envs per GPU (BASELINE.json config 4/5:
+65536 envs per GPU over the 11313-clip AMASS-shaped synthetic library):
+    phc_step_fused      2x motion-state (t, t+1) + imitation reward (+power) + reset + self obs + imitation obs
+                        + RunningNorm.forward output + fp64 column moments            (1 launch)
+    phc_rms_reduce_partials   folds the per-CTA moment partials                           (1 launch)
+    phc_gae             the amortised share of the advantage pass: N elements = N/32 envs x horizon 32  (1 launch)
+    every 32 steps (and at the last timed step): all-reduce of the moments (NCCL, N>1) + phc_rms_finalize.
+Inputs are resident in HBM before the timed region; four input/output sets are rotated so that neither the
+sim state nor the observation buffers are L2-resident between iterations.  The e2e leg runs the same step
+through FusedStep.step_host with pinned HOST buffers (H2D of every per-env input, D2H of reward / flags).
+`--impl reference` times the reference's torch-CPU path (oracle/torch_port.py, validated against the reference's
+golden vectors) on the host cores.  Nothing here reads /root/reference.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+HORIZON = 32
+NUM_CLIPS = 11313
+SETS = 4
+# algorithmic bytes per env-step of phc_step_fused as benchmarked:
+#   reads  1248 sim record + 30 per-env scalars + 24 motion meta + 4 x 1248 reference frames + 2 x 276 dof force/vel
+#   writes 3736 obs + 3736 normalised obs + 4 reward + 20 reward_raw + 2 flags
+STEP_BYTES_READ = 1248 + 30 + 24 + 4 * 1248 + 2 * 276
+STEP_BYTES_WRITE = 3736 + 3736 + 4 + 20 + 2
+STEP_BYTES = STEP_BYTES_READ + STEP_BYTES_WRITE          # 14344
+GAE_BYTES_PER_ELEM = 16
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+    Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "200"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        for ln in self.lines:
+            p = [x.strip() for x in ln.split(",")]
+            if len(p) < 6:
+                continue
+            try:
+                sm.append(float(p[0])); mx.append(float(p[1]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), p[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def measured_peak_gbs():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.isfile(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def cpu_port_rate(n_envs, iters, warmup, threads, tables_host, seed=1):
+    """env-steps/s of the reference torch-CPU path (full step + RunningNorm.forward + the amortised c_gae share)."""
+    import numpy as np
+    import torch
+    from oracle import c_oracle, torch_port as tp
+    from puffer_phc_b200 import synth
+    torch.set_num_threads(threads)
+    S = synth.make_env_state(tables_host, n_envs, seed=seed)
+    R = synth.make_rollout(max(n_envs // HORIZON, 1), HORIZON, seed=2)
+    d, v, r = (R[k].numpy() for k in ("dones", "values", "rewards"))
+    mean, var = torch.zeros(1, 934), torch.ones(1, 934)
+    times = []
+    for i in range(warmup + iters):
+        t0 = time.perf_counter()
+        out = tp.step(tables_host, S)
+        tp.rms_forward(out["obs"], mean, var)
+        c_oracle.gae(d, v, r, 0.98, 0.2)
+        dt = time.perf_counter() - t0
+        if i >= warmup:
+            times.append(dt)
+    return n_envs / statistics.median(times), sum(times)
+
+
+def run_reference(args, rank, world):
+    """The reference arm: the reference's own CPU implementation of the path (torch eager port), all host threads."""
+    if rank != 0:
+        return
+    import torch
+    from puffer_phc_b200 import synth
+    threads = os.cpu_count() or 1
+    sample = 8192
+    T = synth.make_motion_library(NUM_CLIPS, seed=0, device="cpu")
+    torch.set_num_threads(threads)
+    import statistics as st
+    from oracle import c_oracle, torch_port as tp
+    S = synth.make_env_state(T, sample, seed=1)
+    R = synth.make_rollout(sample // HORIZON, HORIZON, seed=2)
+    d, v, r = (R[k].numpy() for k in ("dones", "values", "rewards"))
+    mean, var = torch.zeros(1, 934), torch.ones(1, 934)
+    times = []
+    for i in range(args.warmup + args.steps):
+        t0 = time.perf_counter()
+        out = tp.step(T, S)
+        tp.rms_forward(out["obs"], mean, var)
+        c_oracle.gae(d, v, r, 0.98, 0.2)
+        if i >= args.warmup:
+            times.append(time.perf_counter() - t0)
+    total = sum(times)
+    value = sample * len(times) / total
+    line = {
+        "impl": "reference", "metric": "env_steps_per_s", "value": value, "unit": "env-steps/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / len(times), "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args.envs, world, sample_note=f"each step = a bounded sample of {sample} envs of the workload"),
+        "cpu_baseline": {"value": value, "unit": "env-steps/s", "cores": threads, "kind": "port",
+                         "sample": f"{sample} envs x {len(times)} steps, torch {torch.__version__} eager CPU port of the reference "
+                                   "functions (oracle/torch_port.py) + C c_gae restatement"},
+        "e2e": {"value": value, "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(envs, world, sample_note=None):
+    cfg = {
+        "workload": "config4/5: fused rollout-side step (2x motion-state + imitation obs/reward/reset + self obs + RMS norm "
+                    "+ moments + GAE amortised), 65536 envs per GPU, 11313-clip AMASS-shaped synthetic library",
+        "envs_per_gpu": envs, "global_envs": envs * world, "clips": NUM_CLIPS, "bodies": 24, "obs_dim": 934, "horizon": HORIZON,
+        "gamma": 0.98, "lambda": 0.2, "parallelism": f"env-sharded dp{world}, tables replicated",
+        "l2": f"{SETS} rotating input/output sets (inputs+outputs {SETS} x ~0.6 GB) > 126 MB L2; library gathers are random over 3.1 GB",
+        "rms_update_every": HORIZON,
+    }
+    if sample_note:
+        cfg["sample"] = sample_note
+    return cfg
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=64)
+    ap.add_argument("--warmup", type=int, default=8)
+    ap.add_argument("--envs", type=int, default=65536, help="envs per GPU")
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from puffer_phc_b200 import _ffi, synth
+    from puffer_phc_b200.c_gae import compute_gae_cuda
+    from puffer_phc_b200.dist import init_from_env
+    from puffer_phc_b200.fused_step import FusedStep, StepConfig
+    from puffer_phc_b200.motion_lib import MotionLibSMPL
+    from puffer_phc_b200.policies.running_norm import RunningNorm
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the CUDA kernels are the only implementation (use --impl reference for the CPU arm)")
+    rank, local, world = init_from_env()
+    dev = torch.device("cuda", local)
+    _ffi.load()
+    N, K, W = args.envs, args.steps, args.warmup
+
+    # ---- resident data -----------------------------------------------------------------------------------
+    T = synth.make_motion_library(NUM_CLIPS, seed=0, device=dev)
+    lib = MotionLibSMPL.from_tables(T, device=dev)           # packs the 1248-byte frame records
+    rms = RunningNorm(934).to(dev)
+    fs = FusedStep(lib, N, StepConfig(), rms=rms, normalize=True, accumulate_moments=True)
+    ins, outs = [], []
+    for s in range(SETS):
+        S = synth.make_env_state(T, N, seed=1 + rank + 100 * s)
+        ins.append(S)
+        outs.append({"obs": torch.empty(N, 934, device=dev), "obs_norm": torch.empty(N, 934, device=dev),
+                     "reward": torch.empty(N, device=dev), "reward_raw": torch.empty(N, 5, device=dev),
+                     "reset": torch.empty(N, dtype=torch.bool, device=dev), "terminated": torch.empty(N, dtype=torch.bool, device=dev)})
+    roll = synth.make_rollout(N, HORIZON, seed=2 + rank, device=dev)          # [N*32] flat env-major rollout
+    adv = torch.empty(N * HORIZON, device=dev)
+    # realistic normaliser state: one update from a first observation batch
+    fs(*[ins[0][k] for k in ("body_state", "progress", "start_time", "start_offset", "motion_ids", "global_offset", "dof_force", "dof_vel")], out=outs[0])
+    rms.finalize()
+    torch.cuda.synchronize()
+
+    stream = torch.cuda.current_stream()
+    ev_a = [torch.cuda.Event(enable_timing=True) for _ in range(K)]
+    ev_b = [torch.cuda.Event(enable_timing=True) for _ in range(K)]
+    launches = {"n": 0}
+
+    def one_step(i, timed_idx=None, last=False):
+        S, O = ins[i % SETS], outs[i % SETS]
+        if timed_idx is not None:
+            ev_a[timed_idx].record(stream)
+        fs(S["body_state"], S["progress"], S["start_time"], S["start_offset"], S["motion_ids"], S["global_offset"], S["dof_force"], S["dof_vel"], out=O)
+        if timed_idx is not None:
+            ev_b[timed_idx].record(stream)            # brackets phc_step_fused + the tiny partial reduce
+        lo = (i % HORIZON) * N
+        compute_gae_cuda(roll["dones"][lo:lo + N], roll["values"][lo:lo + N], roll["rewards"][lo:lo + N], 0.98, 0.2, out=adv[lo:lo + N])
+        launches["n"] += 3
+        if (i + 1) % HORIZON == 0 or last:
+            rms.finalize()                             # all-reduce of the fp64 moments (N>1) + running-average update
+            launches["n"] += 2                         # finalize + moments memset
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for i in range(W):
+        one_step(i)
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    launches["n"] = 0
+    t_start, t_stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    t_start.record(stream)
+    for i in range(K):
+        one_step(W + i, timed_idx=i, last=(i == K - 1))
+    t_stop.record(stream)
+    barrier()
+    elapsed_ms = t_start.elapsed_time(t_stop)
+    clocks = sampler.stop() if rank == 0 else None
+    kern_ms = sum(a.elapsed_time(b) for a, b in zip(ev_a, ev_b)) / K
+    if world > 1:
+        t = torch.tensor([elapsed_ms, kern_ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        elapsed_ms, kern_ms = float(t[0]), float(t[1])
+    value = N * world * K / (elapsed_ms * 1e-3)
+
+    # ---- e2e: the public API with HOST buffers (H2D inputs + kernel + D2H results inside the timed region) ---------
+    e2e = None
+    if not args.no_e2e:
+        hin = [{k: v.cpu().pin_memory() for k, v in ins[s].items()} for s in range(2)]
+        for i in range(3):
+            fs.step_host(hin[i % 2])
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        Ke = max(4, min(K, 16))
+        barrier()
+        e0.record(stream)
+        for i in range(Ke):
+            res = fs.step_host(hin[i % 2])
+        e1.record(stream)
+        barrier()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t[0])
+        e2e = {"value": N * world * Ke / (ms * 1e-3), "unit": "env-steps/s", "h2d_bytes_per_step": fs.host_h2d_bytes,
+               "d2h_bytes_per_step": fs.host_d2h_bytes, "ms_per_step": ms / Ke, "steps": Ke,
+               "note": "H2D: PhysX record + per-env scalars + dof force/vel from pinned memory; D2H: reward, reward_raw, reset, "
+                       "terminated (what the reference moves to the host each step, clean_pufferl/structs.py:123-128); obs stays in HBM for the policy"}
+
+    if rank == 0:
+        peak, peak_src = measured_peak_gbs()
+        achieved = STEP_BYTES * N / (kern_ms * 1e-3) / 1e9
+        line = {
+            "metric": "env_steps_per_s", "value": value, "unit": "env-steps/s", "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": elapsed_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic", "config": workload_config(N, world),
+            "roofline": {"bound": "hbm", "kernel": "phc::step_fused_kernel<true>", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                         "algorithmic_bytes_per_env_step": STEP_BYTES, "kernel_ms": kern_ms,
+                         "whole_step_gbs": (STEP_BYTES + GAE_BYTES_PER_ELEM) * N * K / (elapsed_ms * 1e-3) / 1e9},
+            "gpu_launches": launches["n"], "clocks": clocks,
+        }
+        if e2e:
+            line["e2e"] = e2e
+        if world == 1 and not args.no_cpu_baseline:
+            threads = os.cpu_count() or 1
+            host_tables = {k: v.cpu() for k, v in T.items()}
+            sample = 8192
+            rate, spent = cpu_port_rate(sample, iters=5, warmup=2, threads=threads, tables_host=host_tables)
+            line["cpu_baseline"] = {"value": rate, "unit": "env-steps/s", "cores": threads, "kind": "port",
+                                    "sample": f"{sample} envs x 5 steps of the same workload ({spent:.1f} s), torch-CPU eager port of the "
+                                              "reference functions (oracle/torch_port.py) + C c_gae restatement"}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

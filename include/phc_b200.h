@@ -1,0 +1,250 @@
+/*
+ * phc_b200.h -- C ABI of libphc_b200.so: hand-written sm_100a CUDA kernels for the per-step,
+ * data-parallel rollout hot path of howird/puffer-phc.
+ *
+ * The reference has no FFI/plugin registry for this path; its boundary is a Python call surface
+ * (SURVEY.md section 8b).  Each entry point below is what a binding for that surface calls, and
+ * cites the reference function it replaces (paths relative to the reference checkout).  The
+ * ctypes binding that ships with this repo is puffer_phc_b200/_ffi.py; INTEGRATION.md shows the
+ * stub a reference maintainer would add.
+ *
+ * Conventions
+ *  - plain C types only: pointers, sizes, strides; no torch / CUDA types in the signatures
+ *    (a stream is passed as void* holding a cudaStream_t; NULL = legacy default stream).
+ *  - every data pointer is a DEVICE pointer unless its name ends in _h.  The library never
+ *    allocates, frees or retains caller memory; table pointers are borrowed for one call.
+ *  - every function only ENQUEUES work on `stream` and returns; there is no host synchronisation
+ *    and no device->host read inside the library.
+ *  - return value: 0 = PHC_OK; < 0 = argument error (enum below); > 0 = a cudaError_t from the
+ *    launch.  phc_last_error() returns a thread-local description of the last failure.
+ *  - all floating point is IEEE fp32 (kernels are compiled with -fmad=false, precise div/sqrt and
+ *    the precise libm), quaternions are xyzw, index types are int64 like torch.long.
+ *  - J (bodies per env) is 24 for the SMPL humanoid (puffer_phc/body_sets.py:11-36); the stand-alone
+ *    entry points accept 1 <= J <= 32 (body subsets), the fused step requires 24.
+ */
+#ifndef PHC_B200_H
+#define PHC_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PHC_B200_VERSION 100 /* 0.1.0 */
+
+enum {
+    PHC_OK = 0,
+    PHC_EINVAL = -1,       /* NULL where a pointer is required, negative size, bad flag       */
+    PHC_EALIGN = -2,       /* pointer / stride alignment the kernel needs is not met          */
+    PHC_ESHAPE = -3,       /* J, C or L outside the supported range                           */
+    PHC_EUNSUPPORTED = -4  /* semantically valid in the reference but not implemented (e.g. time_steps != 1) */
+};
+
+typedef void *phc_stream_t; /* cudaStream_t */
+
+int phc_version(void);
+const char *phc_last_error(void);
+
+/* A [N, J, C] fp32 tensor whose innermost (component) stride is 1: element (n, j, c) is at
+ * ptr[n * stride_env + j * stride_body + c].  Strides are in floats.  This covers both the
+ * contiguous copies and the strided views of the PhysX AoS rigid-body buffer that the reference
+ * passes (puffer_phc/envs/humanoid_phc.py:542-549).  For a [N, C] tensor stride_body is ignored. */
+typedef struct phc_view {
+    const float *ptr;
+    int64_t stride_env;
+    int64_t stride_body;
+} phc_view;
+
+/* ------------------------------------------------------------------------------------------- */
+/* Motion tables built by MotionLibBase.load_motions (puffer_phc/motion_lib.py:396-420).        */
+/* All contiguous.  F = total frames, M = loaded motions.                                       */
+/* ------------------------------------------------------------------------------------------- */
+typedef struct phc_motion_tables {
+    const float *gts;            /* [F,24,3] global translation                      */
+    const float *grs;            /* [F,24,4] global rotation                         */
+    const float *lrs;            /* [F,24,4] local rotation                          */
+    const float *gvs;            /* [F,24,3] global linear velocity                  */
+    const float *gavs;           /* [F,24,3] global angular velocity                 */
+    const float *dvs;            /* [F,23,3] dof velocity                            */
+    const float *motion_aa;      /* [F,72]   _motion_aa                              */
+    const float *motion_len;     /* [M] _motion_lengths                              */
+    const float *motion_dt;      /* [M] _motion_dt                                   */
+    const int64_t *num_frames;   /* [M] _motion_num_frames                           */
+    const int64_t *length_starts;/* [M] exclusive cumsum of num_frames (:416-419)    */
+    const float *motion_bodies;  /* [M,17] _motion_bodies                            */
+    const float *limb_weights;   /* [M,10] _motion_limb_weights                      */
+    const float *packed;         /* optional [F,312]: per frame gts|grs|gvs|gavs rows back to back, written by
+                                    phc_pack_frames(); NULL = gather from the four separate tables */
+    int64_t F, M;
+} phc_motion_tables;
+
+/* Concatenate the four per-frame rows the step needs into one 1248-byte record per frame
+ * (B200 layout: one contiguous 1248 B gather per frame instead of four 288/384 B ones).
+ * packed: caller-allocated [F,312] fp32, 16-byte aligned. */
+int phc_pack_frames(const phc_motion_tables *t, float *packed, phc_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------- */
+/* MotionLibBase.get_motion_state(motion_ids, motion_times, offset=None)                        */
+/* (puffer_phc/motion_lib.py:549-626) and get_root_pos_smpl (:628-653).                         */
+/* Any output pointer may be NULL (that output is skipped); get_root_pos_smpl = only root_pos.  */
+/* All outputs contiguous [B, ...] fp32.                                                        */
+/* ------------------------------------------------------------------------------------------- */
+typedef struct phc_motion_state_out {
+    float *root_pos;            /* [B,3]    */
+    float *root_rot;            /* [B,4]    */
+    float *dof_pos;             /* [B,69]   */
+    float *root_vel;            /* [B,3]    */
+    float *root_ang_vel;        /* [B,3]    */
+    float *dof_vel;             /* [B,69]   */
+    float *motion_aa;           /* [B,72]   */
+    float *rg_pos;              /* [B,24,3] */
+    float *rb_rot;              /* [B,24,4] */
+    float *body_vel;            /* [B,24,3] */
+    float *body_ang_vel;        /* [B,24,3] */
+    float *motion_bodies;       /* [B,17]   */
+    float *motion_limb_weights; /* [B,10]   */
+    int64_t *frame_idx0;        /* [B] optional: _calc_frame_blend outputs (:655-665) */
+    int64_t *frame_idx1;        /* [B] optional */
+    float *blend;               /* [B] optional */
+} phc_motion_state_out;
+
+int phc_motion_state(const phc_motion_tables *t, const int64_t *motion_ids, const float *motion_times,
+                     const float *offset /* [B,3] or NULL */, int64_t B, const phc_motion_state_out *out,
+                     phc_stream_t stream);
+
+/* MotionLibBase.sample_time_interval arithmetic (puffer_phc/motion_lib.py:526-535); the uniform
+ * phase stays on the caller's torch generator.  out = float(int64((phase*len)/(1/30))) * (1/30).
+ * div_mode 0: IEEE division (torch CPU); 1: multiply by fp32 reciprocal (torch CUDA divides a
+ * tensor by a Python scalar that way).  motion_len is already gathered per sample. */
+int phc_sample_time_interval(const float *phase, const float *motion_len, int64_t n, int div_mode, float *out,
+                             phc_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------- */
+/* puffer_phc/envs/common.py                                                                    */
+/* ------------------------------------------------------------------------------------------- */
+
+/* compute_imitation_observations_v6 (common.py:106-176).  obs: [N, obs_stride >= 24*J], six
+ * body-major blocks [3J,6J,3J,3J,3J,6J].  time_steps must be 1 (the only value the reference
+ * passes, humanoid_phc.py:1097) else PHC_EUNSUPPORTED. */
+int phc_imitation_obs_v6(phc_view root_pos /* [N,3] */, phc_view root_rot /* [N,4] */,
+                         phc_view body_pos, phc_view body_rot, phc_view body_vel, phc_view body_ang_vel,
+                         phc_view ref_body_pos, phc_view ref_body_rot, phc_view ref_body_vel, phc_view ref_body_ang_vel,
+                         int64_t N, int J, int time_steps, int upright, float *obs, int64_t obs_stride,
+                         phc_stream_t stream);
+
+/* compute_humanoid_observations_smpl_max (common.py:23-103) without the smpl / limb-weight
+ * pass-through columns (those are plain concatenations done by the caller).
+ * obs: [N, obs_stride >= (root_height_obs?1:0) + 3(J-1) + 12J]. */
+int phc_self_obs_smpl_max(phc_view body_pos, phc_view body_rot, phc_view body_vel, phc_view body_ang_vel,
+                          int64_t N, int J, int local_root_obs, int root_height_obs, int upright,
+                          float *obs, int64_t obs_stride, phc_stream_t stream);
+
+/* compute_imitation_reward (common.py:270-322).  k, w: HOST arrays of 4 floats in the order
+ * pos, rot, vel, ang_vel (rwd_specs k_* / w_*).  reward [N]; reward_raw [N, raw_stride >= 4]. */
+int phc_imitation_reward(phc_view body_pos, phc_view body_rot, phc_view body_vel, phc_view body_ang_vel,
+                         phc_view ref_body_pos, phc_view ref_body_rot, phc_view ref_body_vel, phc_view ref_body_ang_vel,
+                         int64_t N, int J, const float *k_h, const float *w_h, float *reward, float *reward_raw,
+                         int64_t raw_stride, phc_stream_t stream);
+
+/* compute_humanoid_im_reset (common.py:325-364).  progress: int16 (humanoid_phc.py:571);
+ * pass_time / reset / terminated: 1 byte per env (torch.bool); termination_distance: device [J]
+ * (only element 0 is read when use_mean). */
+int phc_im_reset(const int16_t *progress, phc_view rigid_body_pos, phc_view ref_body_pos, const uint8_t *pass_time,
+                 int enable_early_termination, const float *termination_distance, int use_mean,
+                 int64_t N, int J, uint8_t *reset, uint8_t *terminated, phc_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------- */
+/* The whole post-physics half of HumanoidPHC.step in ONE pass over HBM                          */
+/* (puffer_phc/envs/humanoid_phc.py:136-149: _compute_reward :1228-1303, _compute_reset          */
+/* :1311-1333, _compute_observations :935-959) with the two get_motion_state queries (t, t+1)    */
+/* fused in, plus (optionally) RunningNorm.forward on the fresh observation and the per-column   */
+/* moment partial sums RunningNorm.update needs (puffer_phc/policies/running_norm.py:15-34).     */
+/* ------------------------------------------------------------------------------------------- */
+typedef struct phc_step_in {
+    const float *body_state;     /* PhysX rigid-body tensor, AoS [N, env_stride floats]; body j of env n at
+                                    n*env_stride + 13*j: pos3, rot4 (xyzw), vel3, angvel3   (humanoid_phc.py:542-549) */
+    int64_t env_stride;          /* >= 312 */
+    const int16_t *progress;     /* [N] progress_buf, already incremented (humanoid_phc.py:138)            */
+    const float *start_time;     /* [N] _motion_start_times                                                */
+    const float *start_offset;   /* [N] _motion_start_times_offset                                         */
+    const int64_t *motion_ids;   /* [N] _sampled_motion_ids                                                */
+    const float *global_offset;  /* [N,3] _global_offset                                                   */
+    const float *dof_force;      /* [N,69] or NULL: power reward off (humanoid_phc.py:1295-1303)           */
+    const float *dof_vel;        /* [N,69] or NULL                                                         */
+    const float *term_dist;      /* device [24] _termination_distances, indexed by body id                 */
+    const float *rms_mean;       /* device [934] or NULL (needed iff out.obs_norm != NULL)                 */
+    const float *rms_var;        /* device [934] or NULL                                                   */
+    int64_t N;
+} phc_step_in;
+
+typedef struct phc_step_cfg {
+    float dt;                    /* float32(isaac dt) = 1/30 at defaults (isaacgym_env.py:39-41)           */
+    float k[4], w[4];            /* RewardConfig k_pos,k_rot,k_vel,k_ang_vel / w_* (config.py:25-32)       */
+    float power_coef;            /* rew_power_coef (config.py:96)                                          */
+    uint32_t reset_body_mask;    /* bit j = body j takes part in the termination test (_reset_bodies_id)   */
+    int enable_early_termination;
+    int use_mean;                /* flag_im_eval: mean distance against term_dist[first reset body]        */
+    float rms_eps, rms_clip;     /* RunningNorm epsilon / clip (running_norm.py:6)                         */
+} phc_step_cfg;
+
+typedef struct phc_step_out {
+    float *obs;                  /* [N, obs_stride>=934] raw obs_buf: self 358 | task 576 (humanoid_phc.py:947) */
+    int64_t obs_stride;
+    float *obs_norm;             /* optional [N, obs_stride]: clamp((obs-mean)/sqrt(var+eps), +-clip)       */
+    float *reward;               /* [N] rew_buf                                                            */
+    float *reward_raw;           /* [N, raw_stride]: r_pos,r_rot,r_vel,r_ang_vel[,power]                   */
+    int64_t raw_stride;          /* >= 4, >= 5 with the power reward                                       */
+    uint8_t *reset;              /* [N] reset_buf                                                          */
+    uint8_t *terminated;         /* [N] _terminate_buf                                                     */
+    double *moment_partials;     /* optional [phc_step_num_partials(), 2, 934] fp64: per-CTA sum and sum of
+                                    squares of the raw obs columns; reduce with phc_rms_reduce_partials()  */
+    float *ref_state_t;          /* optional debug [N,312]: blended reference pos72|rot96|vel72|ang72 at t */
+    float *ref_state_t1;         /* optional debug [N,312] at t+1                                          */
+} phc_step_out;
+
+/* number of [2,934] fp64 partial slots phc_step_fused writes (a function of the device only) */
+int phc_step_num_partials(void);
+
+int phc_step_fused(const phc_motion_tables *t, const phc_step_in *in, const phc_step_cfg *cfg,
+                   const phc_step_out *out, phc_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------- */
+/* RunningNorm (puffer_phc/policies/running_norm.py:5-53)                                       */
+/* ------------------------------------------------------------------------------------------- */
+
+/* forward (:15-20): y = clamp((x - mean) / sqrt(var + eps), -clip, clip).  x, y: [B, C] with row
+ * strides in floats; mean, var: device [C]. */
+int phc_rms_forward(const float *x, int64_t x_stride, const float *mean, const float *var, float eps, float clip,
+                    int64_t B, int C, float *y, int64_t y_stride, phc_stream_t stream);
+
+/* update (:23-34), split so that per-rank moments can be all-reduced in between:
+ *   phc_rms_moments         moments[0] += B; moments[1+c] += sum_b x[b,c]; moments[1+C+c] += sum_b x[b,c]^2
+ *                           (fp64, deterministic two-stage reduction; scratch: >= phc_rms_scratch_doubles(C) doubles)
+ *   phc_rms_reduce_partials same accumulation from the per-CTA partials phc_step_fused wrote
+ *   phc_rms_finalize        mean_b = S/n; var_b = SS/n - mean_b^2 (fp64, biased); w = 1/count;
+ *                           running = running*(1-w) + batch*w (fp32, reference op order); count += 1 */
+int64_t phc_rms_scratch_doubles(int C);
+int phc_rms_moments(const float *x, int64_t x_stride, int64_t B, int C, double *moments /* [1+2C] */,
+                    double *scratch, phc_stream_t stream);
+int phc_rms_reduce_partials(const double *partials, int num_partials, int64_t rows, int C, double *moments,
+                            phc_stream_t stream);
+int phc_rms_finalize(const double *moments, int C, float *running_mean, float *running_var, float *count,
+                     phc_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------- */
+/* c_gae.compute_gae(dones, values, rewards, gamma, gae_lambda) (puffer_phc/c_gae.pyx:11-32)    */
+/* Flat serial-scan semantics over the whole array of length L (the carry crosses env           */
+/* boundaries; adv[L-1] = 0; reward/done indexed at t+1).  All arrays device fp32 [L].          */
+/* mode 0 = auto; 1 = blocked scan with a warm-up window (bit-exact whenever the carry decays   */
+/* below fp32 resolution inside the window, which auto verifies from gamma*lambda);             */
+/* 2 = single-thread serial scan (always bit-exact, slow).                                      */
+/* ------------------------------------------------------------------------------------------- */
+int phc_gae(const float *dones, const float *values, const float *rewards, int64_t L, float gamma, float gae_lambda,
+            float *advantages, int mode, phc_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PHC_B200_H */

@@ -1,0 +1,170 @@
+"""ctypes binding of libphc_b200.so (include/phc_b200.h).  No torch types cross the ABI: tensors are passed
+as ``data_ptr()`` integers plus sizes/strides, the stream as ``torch.cuda.current_stream().cuda_stream``.
+
+There is deliberately NO fallback: if the CUDA library cannot be loaded every entry point raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import threading
+
+from . import build as _build
+
+_lock = threading.Lock()
+_lib = None
+
+c_f32p, c_i64p, c_u8p, c_i16p, c_f64p = C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p
+
+EXPORTS = (
+    "phc_version", "phc_last_error", "phc_pack_frames", "phc_motion_state", "phc_sample_time_interval",
+    "phc_imitation_obs_v6", "phc_self_obs_smpl_max", "phc_imitation_reward", "phc_im_reset",
+    "phc_step_num_partials", "phc_step_fused", "phc_rms_forward", "phc_rms_scratch_doubles", "phc_rms_moments",
+    "phc_rms_reduce_partials", "phc_rms_finalize", "phc_gae",
+)
+
+PHC_OK, PHC_EINVAL, PHC_EALIGN, PHC_ESHAPE, PHC_EUNSUPPORTED = 0, -1, -2, -3, -4
+
+
+class View(C.Structure):
+    """phc_view: [N, J, C] fp32 tensor with unit innermost stride (strides in floats)."""
+    _fields_ = [("ptr", C.c_void_p), ("stride_env", C.c_int64), ("stride_body", C.c_int64)]
+
+
+TABLE_FIELDS = ("gts", "grs", "lrs", "gvs", "gavs", "dvs", "motion_aa", "motion_len", "motion_dt", "num_frames",
+                "length_starts", "motion_bodies", "limb_weights", "packed")
+
+
+class MotionTables(C.Structure):
+    _fields_ = [(k, C.c_void_p) for k in TABLE_FIELDS] + [("F", C.c_int64), ("M", C.c_int64)]
+
+
+STATE_FIELDS = ("root_pos", "root_rot", "dof_pos", "root_vel", "root_ang_vel", "dof_vel", "motion_aa", "rg_pos", "rb_rot",
+                "body_vel", "body_ang_vel", "motion_bodies", "motion_limb_weights", "frame_idx0", "frame_idx1", "blend")
+
+
+class MotionStateOut(C.Structure):
+    _fields_ = [(k, C.c_void_p) for k in STATE_FIELDS]
+
+
+class StepIn(C.Structure):
+    _fields_ = [
+        ("body_state", C.c_void_p), ("env_stride", C.c_int64), ("progress", C.c_void_p), ("start_time", C.c_void_p),
+        ("start_offset", C.c_void_p), ("motion_ids", C.c_void_p), ("global_offset", C.c_void_p), ("dof_force", C.c_void_p),
+        ("dof_vel", C.c_void_p), ("term_dist", C.c_void_p), ("rms_mean", C.c_void_p), ("rms_var", C.c_void_p), ("N", C.c_int64),
+    ]
+
+
+class StepCfg(C.Structure):
+    _fields_ = [
+        ("dt", C.c_float), ("k", C.c_float * 4), ("w", C.c_float * 4), ("power_coef", C.c_float),
+        ("reset_body_mask", C.c_uint32), ("enable_early_termination", C.c_int), ("use_mean", C.c_int),
+        ("rms_eps", C.c_float), ("rms_clip", C.c_float),
+    ]
+
+
+class StepOut(C.Structure):
+    _fields_ = [
+        ("obs", C.c_void_p), ("obs_stride", C.c_int64), ("obs_norm", C.c_void_p), ("reward", C.c_void_p),
+        ("reward_raw", C.c_void_p), ("raw_stride", C.c_int64), ("reset", C.c_void_p), ("terminated", C.c_void_p),
+        ("moment_partials", C.c_void_p), ("ref_state_t", C.c_void_p), ("ref_state_t1", C.c_void_p),
+    ]
+
+
+def _declare(lib):
+    P, I64, I, F = C.c_void_p, C.c_int64, C.c_int, C.c_float
+    lib.phc_version.argtypes, lib.phc_version.restype = [], I
+    lib.phc_last_error.argtypes, lib.phc_last_error.restype = [], C.c_char_p
+    lib.phc_pack_frames.argtypes = [C.POINTER(MotionTables), P, P]
+    lib.phc_motion_state.argtypes = [C.POINTER(MotionTables), P, P, P, I64, C.POINTER(MotionStateOut), P]
+    lib.phc_sample_time_interval.argtypes = [P, P, I64, I, P, P]
+    lib.phc_imitation_obs_v6.argtypes = [View] * 10 + [I64, I, I, I, P, I64, P]
+    lib.phc_self_obs_smpl_max.argtypes = [View] * 4 + [I64, I, I, I, I, P, I64, P]
+    lib.phc_imitation_reward.argtypes = [View] * 8 + [I64, I, C.POINTER(F), C.POINTER(F), P, P, I64, P]
+    lib.phc_im_reset.argtypes = [P, View, View, P, I, P, I, I64, I, P, P, P]
+    lib.phc_step_num_partials.argtypes, lib.phc_step_num_partials.restype = [], I
+    lib.phc_step_fused.argtypes = [C.POINTER(MotionTables), C.POINTER(StepIn), C.POINTER(StepCfg), C.POINTER(StepOut), P]
+    lib.phc_rms_forward.argtypes = [P, I64, P, P, F, F, I64, I, P, I64, P]
+    lib.phc_rms_scratch_doubles.argtypes, lib.phc_rms_scratch_doubles.restype = [I], I64
+    lib.phc_rms_moments.argtypes = [P, I64, I64, I, P, P, P]
+    lib.phc_rms_reduce_partials.argtypes = [P, I, I64, I, P, P]
+    lib.phc_rms_finalize.argtypes = [P, I, P, P, P, P]
+    lib.phc_gae.argtypes = [P, P, P, I64, F, F, P, I, P]
+    for name in EXPORTS:
+        fn = getattr(lib, name)
+        if fn.restype is C.c_int and name not in ("phc_version", "phc_step_num_partials"):
+            fn.restype = I
+
+
+def library_path() -> str:
+    return _build.LIB_PATH
+
+
+def load() -> C.CDLL:
+    """Load (building if necessary) libphc_b200.so; raises RuntimeError if that is impossible."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    with _lock:
+        if _lib is None:
+            path = _build.LIB_PATH
+            if not os.path.isfile(path) or _build.needs_build():
+                try:
+                    _build.build()
+                except Exception as exc:  # no nvcc and no prebuilt library
+                    if not os.path.isfile(path):
+                        raise RuntimeError(
+                            f"libphc_b200.so is missing and could not be built ({exc}); the CUDA kernels are the only "
+                            "implementation of this package -- there is no CPU fallback") from exc
+            lib = C.CDLL(path)
+            _declare(lib)
+            if lib.phc_version() != 100:
+                raise RuntimeError(f"libphc_b200.so version {lib.phc_version()} does not match the Python package")
+            _lib = lib
+    return _lib
+
+
+def check(rc: int, what: str = "") -> None:
+    if rc != 0:
+        msg = load().phc_last_error().decode("utf-8", "replace")
+        kind = {PHC_EINVAL: "invalid argument", PHC_EALIGN: "alignment", PHC_ESHAPE: "shape",
+                PHC_EUNSUPPORTED: "unsupported"}.get(rc, f"CUDA error {rc}")
+        if rc == PHC_EUNSUPPORTED:
+            raise NotImplementedError(f"{what or 'libphc_b200'}: {msg}")
+        if rc < 0:
+            raise ValueError(f"{what or 'libphc_b200'} ({kind}): {msg}")
+        raise RuntimeError(f"{what or 'libphc_b200'} ({kind}): {msg}")
+
+
+def require_cuda(*tensors):
+    """The product path is CUDA-only: fail loudly rather than compute anything on the host."""
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError("puffer_phc_b200: expected CUDA tensors -- the kernels are the only implementation "
+                               f"(got a tensor on {t.device})")
+
+
+def stream_ptr():
+    import torch
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def ptr(t):
+    return C.c_void_p(None if t is None else t.data_ptr())
+
+
+def view3(t) -> View:
+    """[N, J, C] (or [N, C]) fp32 tensor with unit inner stride -> phc_view; other layouts must be made contiguous first."""
+    if t.dim() == 2:
+        return View(t.data_ptr(), t.stride(0), 0)
+    return View(t.data_ptr(), t.stride(0), t.stride(1))
+
+
+def as_view_tensor(t):
+    """Return a tensor that phc_view can describe without copying when possible (fp32, unit inner stride)."""
+    import torch
+    if t.dtype != torch.float32:
+        t = t.float()
+    if t.stride(-1) != 1 and t.shape[-1] != 1:
+        t = t.contiguous()
+    return t

@@ -1,0 +1,133 @@
+// gae.cu -- c_gae.compute_gae (reference puffer_phc/c_gae.pyx:11-32): a serial reverse scan over the
+// WHOLE flat rollout array (the carry crosses env boundaries), reward/done indexed at t+1, adv[L-1] = 0:
+//     nnt  = 1 - dones[t+1]
+//     d    = (rewards[t+1] + (gamma * values[t+1]) * nnt) - values[t]
+//     last = d + ((gamma * lambda) * nnt) * last          adv[t] = last
+//
+// Blocked kernel: each thread owns 32 consecutive elements and runs the SAME sequential recurrence, after
+// a warm-up over the K elements to its right started from last = 0.  The unknown true carry enters the
+// warm-up multiplied by prod(gamma*lambda*nnt) <= (gamma*lambda)^K, which the host chooses below 2^-40, far
+// under fp32 resolution (and exactly 0 after any done), so the chunk starts from the exact carry and the
+// output is bit-identical to the serial scan; chunks whose window reaches the end of the array are exact by
+// construction.  Tiles are staged in shared memory with coalesced loads/stores (stride-33 padding).
+// Serial kernel: one thread, used when gamma*lambda is too close to 1 for a bounded window.
+#include "phc_common.cuh"
+
+namespace phc {
+
+constexpr int GAE_CH = 32;          // elements per thread
+constexpr int GAE_THREADS = 64;     // threads per CTA -> 2048-element tiles
+constexpr int GAE_TILE = GAE_CH * GAE_THREADS;
+constexpr int GAE_KMAX = 2048;
+
+__device__ __forceinline__ int pad33(int i) { return i + (i >> 5); }
+
+__global__ void __launch_bounds__(GAE_THREADS) gae_blocked_kernel(const float* __restrict__ dones, const float* __restrict__ values,
+                                                                  const float* __restrict__ rewards, int64_t L, float gamma,
+                                                                  float gl, int K, float* __restrict__ adv) {
+    extern __shared__ float sm[];
+    const int span = GAE_TILE + K + 1;                 // elements [tile0, tile0 + span) are needed
+    const int pspan = pad33(span) + 1;
+    float* s_d = sm;
+    float* s_v = s_d + pspan;
+    float* s_r = s_v + pspan;
+    float* s_a = s_r + pspan;                          // [pad33(GAE_TILE)+1]
+    const int64_t tile0 = (int64_t)blockIdx.x * GAE_TILE;
+    const int64_t avail = (L - tile0 < span) ? (L - tile0) : span;
+    for (int i = threadIdx.x; i < avail; i += GAE_THREADS) {
+        const int p = pad33(i);
+        s_d[p] = __ldg(dones + tile0 + i);
+        s_v[p] = __ldg(values + tile0 + i);
+        s_r[p] = __ldg(rewards + tile0 + i);
+    }
+    __syncthreads();
+    const int c0 = threadIdx.x * GAE_CH;               // chunk [c0, c0+32) relative to the tile
+    if (tile0 + c0 < L) {
+        // highest t_cur this thread evaluates: warm-up start, clipped to L-2 (adv[L-1] = 0 starts the true scan)
+        int64_t hi = tile0 + c0 + GAE_CH - 1 + K;
+        if (hi > L - 2) hi = L - 2;
+        float last = 0.0f;
+        for (int i = (int)(hi - tile0); i >= c0; --i) {
+            const int pn = pad33(i + 1), pc = pad33(i);
+            const float nnt = 1.0f - s_d[pn];
+            const float delta = (s_r[pn] + (gamma * s_v[pn]) * nnt) - s_v[pc];
+            last = delta + (gl * nnt) * last;
+            if (i < c0 + GAE_CH) s_a[pc] = last;
+        }
+        if (tile0 + c0 + GAE_CH > L - 1 && tile0 + c0 <= L - 1) s_a[pad33((int)(L - 1 - tile0))] = 0.0f;
+    }
+    __syncthreads();
+    const int64_t nout = (L - tile0 < GAE_TILE) ? (L - tile0) : GAE_TILE;
+    for (int i = threadIdx.x; i < nout; i += GAE_THREADS) adv[tile0 + i] = s_a[pad33(i)];
+}
+
+// one warp: coalesced staging of 1024-element chunks, lane 0 runs the recurrence.
+constexpr int GAE_SER_CHUNK = 1024;
+__global__ void __launch_bounds__(32) gae_serial_kernel(const float* __restrict__ dones, const float* __restrict__ values,
+                                                        const float* __restrict__ rewards, int64_t L, float gamma, float gl,
+                                                        float* __restrict__ adv) {
+    __shared__ float s_d[GAE_SER_CHUNK + 1], s_v[GAE_SER_CHUNK + 1], s_r[GAE_SER_CHUNK + 1], s_a[GAE_SER_CHUNK];
+    const int lane = threadIdx.x;
+    float last = 0.0f;
+    if (lane == 0) adv[L - 1] = 0.0f;
+    // chunks of t_cur in [lo, hi), walking down from L-1 (exclusive)
+    for (int64_t hi = L - 1; hi > 0; hi -= GAE_SER_CHUNK) {
+        const int64_t lo = hi > GAE_SER_CHUNK ? hi - GAE_SER_CHUNK : 0;
+        const int n = (int)(hi - lo);
+        for (int i = lane; i <= n; i += 32) {          // needs elements [lo, hi]
+            s_d[i] = __ldg(dones + lo + i);
+            s_v[i] = __ldg(values + lo + i);
+            s_r[i] = __ldg(rewards + lo + i);
+        }
+        __syncwarp();
+        if (lane == 0)
+            for (int i = n - 1; i >= 0; --i) {
+                const float nnt = 1.0f - s_d[i + 1];
+                const float delta = (s_r[i + 1] + (gamma * s_v[i + 1]) * nnt) - s_v[i];
+                last = delta + (gl * nnt) * last;
+                s_a[i] = last;
+            }
+        __syncwarp();
+        for (int i = lane; i < n; i += 32) adv[lo + i] = s_a[i];
+        __syncwarp();
+    }
+}
+
+}  // namespace phc
+
+using namespace phc;
+
+extern "C" int phc_gae(const float* dones, const float* values, const float* rewards, int64_t L, float gamma, float gae_lambda,
+                       float* advantages, int mode, phc_stream_t stream) {
+    const char* fn = "phc_gae";
+    PHC_REQUIRE(L >= 0, PHC_EINVAL, "%s: L < 0", fn);
+    PHC_REQUIRE(mode >= 0 && mode <= 2, PHC_EINVAL, "%s: mode must be 0, 1 or 2", fn);
+    if (L == 0) return PHC_OK;
+    PHC_REQUIRE(dones && values && rewards && advantages, PHC_EINVAL, "%s: NULL pointer", fn);
+    cudaStream_t s = (cudaStream_t)stream;
+    const float gl = gamma * gae_lambda;                  // formed in fp32 like the reference's C floats
+    // warm-up window: (|gl|)^K <= 2^-40
+    int K = -1;
+    const float agl = fabsf(gl);
+    if (agl == 0.0f) K = GAE_CH;
+    else if (agl < 1.0f) {
+        const double k = 40.0 * 0.6931471805599453 / -log((double)agl);
+        if (k <= (double)GAE_KMAX) { K = ((int)ceil(k) + GAE_CH - 1) / GAE_CH * GAE_CH; if (K < GAE_CH) K = GAE_CH; }
+    }
+    if (mode == 1 && K < 0) return fail(PHC_EUNSUPPORTED, "%s: gamma*lambda=%g needs a warm-up window > %d; use mode 0 or 2", fn, (double)gl, GAE_KMAX);
+    if (mode == 2 || K < 0) {
+        gae_serial_kernel<<<1, 32, 0, s>>>(dones, values, rewards, L, gamma, gl, advantages);
+        return check_launch(fn);
+    }
+    const int span = GAE_TILE + K + 1;
+    const size_t smem = (size_t)(3 * ((span + (span >> 5)) + 1) + (GAE_TILE + (GAE_TILE >> 5)) + 1) * sizeof(float);
+    static thread_local size_t configured = 0;
+    if (smem > 48 * 1024 && smem > configured) {
+        cudaError_t e = cudaFuncSetAttribute(gae_blocked_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return fail((int)e, "%s: cudaFuncSetAttribute: %s", fn, cudaGetErrorString(e));
+        configured = smem;
+    }
+    const int64_t tiles = (L + GAE_TILE - 1) / GAE_TILE;
+    gae_blocked_kernel<<<(unsigned)tiles, GAE_THREADS, smem, s>>>(dones, values, rewards, L, gamma, gl, K, advantages);
+    return check_launch(fn);
+}

@@ -1,0 +1,194 @@
+// imitation.cu -- stand-alone drop-ins for the four free functions of reference puffer_phc/envs/common.py:
+// compute_imitation_observations_v6 (:106-176), compute_humanoid_observations_smpl_max (:23-103),
+// compute_imitation_reward (:270-322), compute_humanoid_im_reset (:325-364).
+//
+// One warp per env, lane j = body j (J <= 32).  Inputs are strided views (phc_view) so the PhysX AoS
+// buffer slices the reference passes are consumed in place; the heading quaternion is computed once per
+// env; body reductions are warp shuffles.  (The fused step kernel in step_fused.cu shares the same
+// per-body math through phc_body.cuh.)
+#include "phc_body.cuh"
+
+namespace phc {
+
+constexpr int IM_WARPS = 4;
+
+__device__ __forceinline__ const float* at(const phc_view& v, int64_t n, int j) { return v.ptr + n * v.stride_env + (int64_t)j * v.stride_body; }
+
+struct ObsArgs {
+    phc_view root_pos, root_rot, pos, rot, vel, ang, rpos, rrot, rvel, rang;
+    int64_t N; int J; int upright; float* obs; int64_t obs_stride;
+};
+
+__global__ void __launch_bounds__(IM_WARPS * 32) imitation_obs_kernel(const ObsArgs a) {
+    const int lane = threadIdx.x & 31;
+    const int64_t n = (int64_t)blockIdx.x * IM_WARPS + (threadIdx.x >> 5);
+    if (n >= a.N) return;
+    Q4 rr = ld4(a.root_rot.ptr + n * a.root_rot.stride_env);
+    if (!a.upright) rr = remove_base_rot(rr);
+    float hz, hw;
+    heading_quat(calc_heading(rr), hz, hw);                      // h = (0,0,hz,hw), h^-1 = (0,0,-hz,hw)
+    const V3 rp = ld3(a.root_pos.ptr + n * a.root_pos.stride_env);
+    if (lane >= a.J) return;
+    const int j = lane, J = a.J;
+    BodyState b{ld3(at(a.pos, n, j)), ld4(at(a.rot, n, j)), ld3(at(a.vel, n, j)), ld3(at(a.ang, n, j))};
+    BodyState r{ld3(at(a.rpos, n, j)), ld4(at(a.rrot, n, j)), ld3(at(a.rvel, n, j)), ld3(at(a.rang, n, j))};
+    float* o = a.obs + n * a.obs_stride;
+    task_obs_body(b, r, rp, hz, hw, o + 3 * j, o + 3 * J + 6 * j, o + 9 * J + 3 * j, o + 12 * J + 3 * j, o + 15 * J + 3 * j,
+                  o + 18 * J + 6 * j);
+}
+
+struct SelfArgs {
+    phc_view pos, rot, vel, ang;
+    int64_t N; int J; int local_root_obs, root_height_obs, upright; float* obs; int64_t obs_stride;
+};
+
+__global__ void __launch_bounds__(IM_WARPS * 32) self_obs_kernel(const SelfArgs a) {
+    const int lane = threadIdx.x & 31;
+    const int64_t n = (int64_t)blockIdx.x * IM_WARPS + (threadIdx.x >> 5);
+    if (n >= a.N) return;
+    Q4 rr = ld4(at(a.rot, n, 0));
+    if (!a.upright) rr = remove_base_rot(rr);                    // common.py:41-42
+    float hz, hw;
+    heading_quat(calc_heading(rr), hz, hw);
+    const V3 rp = ld3(at(a.pos, n, 0));
+    if (lane >= a.J) return;
+    const int j = lane, J = a.J;
+    float* o = a.obs + n * a.obs_stride;
+    if (a.root_height_obs) { if (j == 0) o[0] = rp.z; o += 1; }  // common.py:40, 92-93
+    BodyState b{ld3(at(a.pos, n, j)), ld4(at(a.rot, n, j)), ld3(at(a.vel, n, j)), ld3(at(a.ang, n, j))};
+    float* rot_out = o + 3 * (J - 1) + 6 * j;
+    self_obs_body(b, rp, hz, hw, j, o + 3 * (j - 1), rot_out, o + 3 * (J - 1) + 6 * J + 3 * j, o + 3 * (J - 1) + 9 * J + 3 * j);
+    if (!a.local_root_obs && j == 0) tan_norm(rr, rot_out);      // common.py:77-79
+}
+
+struct RewardArgs {
+    phc_view pos, rot, vel, ang, rpos, rrot, rvel, rang;
+    int64_t N; int J; float k[4], w[4]; float* reward; float* raw; int64_t raw_stride;
+};
+
+__global__ void __launch_bounds__(IM_WARPS * 32) reward_kernel(const RewardArgs a) {
+    const int lane = threadIdx.x & 31;
+    const int64_t n = (int64_t)blockIdx.x * IM_WARPS + (threadIdx.x >> 5);
+    if (n >= a.N) return;
+    float sp = 0.0f, sr = 0.0f, sv = 0.0f, sa = 0.0f;
+    if (lane < a.J) {
+        const int j = lane;
+        BodyState b{ld3(at(a.pos, n, j)), ld4(at(a.rot, n, j)), ld3(at(a.vel, n, j)), ld3(at(a.ang, n, j))};
+        BodyState r{ld3(at(a.rpos, n, j)), ld4(at(a.rrot, n, j)), ld3(at(a.rvel, n, j)), ld3(at(a.rang, n, j))};
+        reward_terms_body(b, r, sp, sr, sv, sa);
+    }
+    sp = warp_sum(sp); sr = warp_sum(sr); sv = warp_sum(sv); sa = warp_sum(sa);
+    if (lane == 0) {
+        float raw[4];
+        a.reward[n] = reward_from_sums(sp, sr, sv, sa, (float)a.J, a.k, a.w, raw);
+        float* o = a.raw + n * a.raw_stride;
+        o[0] = raw[0]; o[1] = raw[1]; o[2] = raw[2]; o[3] = raw[3];
+    }
+}
+
+struct ResetArgs {
+    const int16_t* progress; phc_view pos, rpos; const uint8_t* pass_time; int early; const float* term_dist; int use_mean;
+    int64_t N; int J; uint8_t* reset; uint8_t* terminated;
+};
+
+__global__ void __launch_bounds__(IM_WARPS * 32) reset_kernel(const ResetArgs a) {
+    const int lane = threadIdx.x & 31;
+    const int64_t n = (int64_t)blockIdx.x * IM_WARPS + (threadIdx.x >> 5);
+    if (n >= a.N) return;
+    bool fallen = false;
+    if (a.early) {
+        float d = 0.0f;
+        bool over = false;
+        if (lane < a.J) {
+            d = norm3(ld3(at(a.pos, n, lane)) - ld3(at(a.rpos, n, lane)));
+            over = d > __ldg(a.term_dist + (a.use_mean ? 0 : lane));
+        }
+        if (a.use_mean) fallen = (warp_sum(d) / (float)a.J) > __ldg(a.term_dist);   // common.py:342-346
+        else fallen = __any_sync(FULL, over);                                          // common.py:347-350
+        fallen = fallen && (a.progress[n] > 1);                                        // common.py:354
+    }
+    if (lane == 0) {
+        a.terminated[n] = fallen ? 1 : 0;                                              // common.py:356
+        a.reset[n] = a.pass_time[n] ? 1 : (fallen ? 1 : 0);                            // common.py:362
+    }
+}
+
+static int check_view(const char* fn, const char* name, const phc_view& v) {
+    if (!v.ptr) return fail(PHC_EINVAL, "%s: %s is NULL", fn, name);
+    return PHC_OK;
+}
+
+}  // namespace phc
+
+using namespace phc;
+
+#define CHECK_VIEW(fn, v) do { int rc_ = check_view(fn, #v, v); if (rc_) return rc_; } while (0)
+
+extern "C" int phc_imitation_obs_v6(phc_view root_pos, phc_view root_rot, phc_view body_pos, phc_view body_rot,
+                                    phc_view body_vel, phc_view body_ang_vel, phc_view ref_body_pos, phc_view ref_body_rot,
+                                    phc_view ref_body_vel, phc_view ref_body_ang_vel, int64_t N, int J, int time_steps,
+                                    int upright, float* obs, int64_t obs_stride, phc_stream_t stream) {
+    const char* fn = "phc_imitation_obs_v6";
+    PHC_REQUIRE(N >= 0, PHC_EINVAL, "%s: N < 0", fn);
+    PHC_REQUIRE(time_steps == 1, PHC_EUNSUPPORTED, "%s: time_steps=%d (only 1 is implemented; the reference never passes another value)", fn, time_steps);
+    PHC_REQUIRE(J >= 1 && J <= 32, PHC_ESHAPE, "%s: J=%d outside [1,32]", fn, J);
+    if (N == 0) return PHC_OK;
+    CHECK_VIEW(fn, root_pos); CHECK_VIEW(fn, root_rot); CHECK_VIEW(fn, body_pos); CHECK_VIEW(fn, body_rot);
+    CHECK_VIEW(fn, body_vel); CHECK_VIEW(fn, body_ang_vel); CHECK_VIEW(fn, ref_body_pos); CHECK_VIEW(fn, ref_body_rot);
+    CHECK_VIEW(fn, ref_body_vel); CHECK_VIEW(fn, ref_body_ang_vel);
+    PHC_REQUIRE(obs, PHC_EINVAL, "%s: obs is NULL", fn);
+    PHC_REQUIRE(obs_stride >= 24 * J, PHC_ESHAPE, "%s: obs_stride=%lld < 24*J", fn, (long long)obs_stride);
+    ObsArgs a{root_pos, root_rot, body_pos, body_rot, body_vel, body_ang_vel, ref_body_pos, ref_body_rot, ref_body_vel,
+              ref_body_ang_vel, N, J, upright, obs, obs_stride};
+    imitation_obs_kernel<<<(unsigned)((N + IM_WARPS - 1) / IM_WARPS), IM_WARPS * 32, 0, (cudaStream_t)stream>>>(a);
+    return check_launch(fn);
+}
+
+extern "C" int phc_self_obs_smpl_max(phc_view body_pos, phc_view body_rot, phc_view body_vel, phc_view body_ang_vel,
+                                     int64_t N, int J, int local_root_obs, int root_height_obs, int upright, float* obs,
+                                     int64_t obs_stride, phc_stream_t stream) {
+    const char* fn = "phc_self_obs_smpl_max";
+    PHC_REQUIRE(N >= 0, PHC_EINVAL, "%s: N < 0", fn);
+    PHC_REQUIRE(J >= 1 && J <= 32, PHC_ESHAPE, "%s: J=%d outside [1,32]", fn, J);
+    if (N == 0) return PHC_OK;
+    CHECK_VIEW(fn, body_pos); CHECK_VIEW(fn, body_rot); CHECK_VIEW(fn, body_vel); CHECK_VIEW(fn, body_ang_vel);
+    PHC_REQUIRE(obs, PHC_EINVAL, "%s: obs is NULL", fn);
+    PHC_REQUIRE(obs_stride >= (root_height_obs ? 1 : 0) + 3 * (J - 1) + 12 * J, PHC_ESHAPE, "%s: obs_stride too small", fn);
+    SelfArgs a{body_pos, body_rot, body_vel, body_ang_vel, N, J, local_root_obs, root_height_obs, upright, obs, obs_stride};
+    self_obs_kernel<<<(unsigned)((N + IM_WARPS - 1) / IM_WARPS), IM_WARPS * 32, 0, (cudaStream_t)stream>>>(a);
+    return check_launch(fn);
+}
+
+extern "C" int phc_imitation_reward(phc_view body_pos, phc_view body_rot, phc_view body_vel, phc_view body_ang_vel,
+                                    phc_view ref_body_pos, phc_view ref_body_rot, phc_view ref_body_vel,
+                                    phc_view ref_body_ang_vel, int64_t N, int J, const float* k_h, const float* w_h,
+                                    float* reward, float* reward_raw, int64_t raw_stride, phc_stream_t stream) {
+    const char* fn = "phc_imitation_reward";
+    PHC_REQUIRE(N >= 0, PHC_EINVAL, "%s: N < 0", fn);
+    PHC_REQUIRE(J >= 1 && J <= 32, PHC_ESHAPE, "%s: J=%d outside [1,32]", fn, J);
+    if (N == 0) return PHC_OK;
+    CHECK_VIEW(fn, body_pos); CHECK_VIEW(fn, body_rot); CHECK_VIEW(fn, body_vel); CHECK_VIEW(fn, body_ang_vel);
+    CHECK_VIEW(fn, ref_body_pos); CHECK_VIEW(fn, ref_body_rot); CHECK_VIEW(fn, ref_body_vel); CHECK_VIEW(fn, ref_body_ang_vel);
+    PHC_REQUIRE(k_h && w_h && reward && reward_raw, PHC_EINVAL, "%s: NULL pointer", fn);
+    PHC_REQUIRE(raw_stride >= 4, PHC_ESHAPE, "%s: raw_stride < 4", fn);
+    RewardArgs a{body_pos, body_rot, body_vel, body_ang_vel, ref_body_pos, ref_body_rot, ref_body_vel, ref_body_ang_vel, N, J,
+                 {k_h[0], k_h[1], k_h[2], k_h[3]}, {w_h[0], w_h[1], w_h[2], w_h[3]}, reward, reward_raw, raw_stride};
+    reward_kernel<<<(unsigned)((N + IM_WARPS - 1) / IM_WARPS), IM_WARPS * 32, 0, (cudaStream_t)stream>>>(a);
+    return check_launch(fn);
+}
+
+extern "C" int phc_im_reset(const int16_t* progress, phc_view rigid_body_pos, phc_view ref_body_pos, const uint8_t* pass_time,
+                            int enable_early_termination, const float* termination_distance, int use_mean, int64_t N, int J,
+                            uint8_t* reset, uint8_t* terminated, phc_stream_t stream) {
+    const char* fn = "phc_im_reset";
+    PHC_REQUIRE(N >= 0, PHC_EINVAL, "%s: N < 0", fn);
+    PHC_REQUIRE(J >= 1 && J <= 32, PHC_ESHAPE, "%s: J=%d outside [1,32]", fn, J);
+    if (N == 0) return PHC_OK;
+    CHECK_VIEW(fn, rigid_body_pos); CHECK_VIEW(fn, ref_body_pos);
+    PHC_REQUIRE(progress && pass_time && reset && terminated, PHC_EINVAL, "%s: NULL pointer", fn);
+    PHC_REQUIRE(!enable_early_termination || termination_distance, PHC_EINVAL, "%s: termination_distance is NULL", fn);
+    ResetArgs a{progress, rigid_body_pos, ref_body_pos, pass_time, enable_early_termination, termination_distance, use_mean,
+                N, J, reset, terminated};
+    reset_kernel<<<(unsigned)((N + IM_WARPS - 1) / IM_WARPS), IM_WARPS * 32, 0, (cudaStream_t)stream>>>(a);
+    return check_launch(fn);
+}

@@ -1,0 +1,164 @@
+// motion_state.cu -- MotionLibBase.get_motion_state / get_root_pos_smpl / sample_time_interval
+// (reference puffer_phc/motion_lib.py:526-535, 549-665) and the packed-frame table builder.
+//
+// One warp per query, lane j = body j: frame-index/blend (bit-exact op order), the row gathers of the
+// two bracketing frames, lerp of pos/vel/ang-vel/dof-vel, slerp of global and local rotations and
+// the quaternion -> exp-map of the local rotations, all in one pass; nothing is materialised.
+#include "phc_common.cuh"
+
+namespace phc {
+
+struct StateArgs {
+    phc_motion_tables t;
+    const int64_t* ids;
+    const float* times;
+    const float* offset;
+    int64_t B;
+    phc_motion_state_out o;
+};
+
+constexpr int MS_WARPS = 4;
+
+__global__ void __launch_bounds__(MS_WARPS * 32) motion_state_kernel(const StateArgs a) {
+    const int lane = threadIdx.x & 31;
+    const int64_t q = (int64_t)blockIdx.x * MS_WARPS + (threadIdx.x >> 5);
+    if (q >= a.B) return;
+    const phc_motion_tables& T = a.t;
+    const phc_motion_state_out& o = a.o;
+
+    const int64_t id = __ldg(a.ids + q);
+    const float time = __ldg(a.times + q);
+    int64_t i0, i1;
+    float blend;
+    frame_blend(time, __ldg(T.motion_len + id), __ldg(T.num_frames + id), __ldg(T.motion_dt + id), i0, i1, blend);
+    const int64_t ls = __ldg(T.length_starts + id);
+    const int64_t f0 = i0 + ls, f1 = i1 + ls;
+    const float one_m = 1.0f - blend;
+    if (lane == 0) {
+        if (o.frame_idx0) o.frame_idx0[q] = i0;
+        if (o.frame_idx1) o.frame_idx1[q] = i1;
+        if (o.blend) o.blend[q] = blend;
+    }
+
+    if (lane < NB) {
+        const int j = lane;
+        if (o.rg_pos || o.root_pos) {
+            V3 p0 = ldg3(T.gts + (f0 * NB + j) * 3), p1 = ldg3(T.gts + (f1 * NB + j) * 3);
+            V3 p{lerp(p0.x, p1.x, one_m, blend), lerp(p0.y, p1.y, one_m, blend), lerp(p0.z, p1.z, one_m, blend)};
+            if (a.offset) {   // motion_lib.py:599: (lerp) + offset
+                p.x = p.x + __ldg(a.offset + q * 3 + 0);
+                p.y = p.y + __ldg(a.offset + q * 3 + 1);
+                p.z = p.z + __ldg(a.offset + q * 3 + 2);
+            }
+            if (o.rg_pos) st3(o.rg_pos + (q * NB + j) * 3, p);
+            if (o.root_pos && j == 0) st3(o.root_pos + q * 3, p);
+        }
+        if (o.body_vel || o.root_vel) {
+            V3 p0 = ldg3(T.gvs + (f0 * NB + j) * 3), p1 = ldg3(T.gvs + (f1 * NB + j) * 3);
+            V3 p{lerp(p0.x, p1.x, one_m, blend), lerp(p0.y, p1.y, one_m, blend), lerp(p0.z, p1.z, one_m, blend)};
+            if (o.body_vel) st3(o.body_vel + (q * NB + j) * 3, p);
+            if (o.root_vel && j == 0) st3(o.root_vel + q * 3, p);
+        }
+        if (o.body_ang_vel || o.root_ang_vel) {
+            V3 p0 = ldg3(T.gavs + (f0 * NB + j) * 3), p1 = ldg3(T.gavs + (f1 * NB + j) * 3);
+            V3 p{lerp(p0.x, p1.x, one_m, blend), lerp(p0.y, p1.y, one_m, blend), lerp(p0.z, p1.z, one_m, blend)};
+            if (o.body_ang_vel) st3(o.body_ang_vel + (q * NB + j) * 3, p);
+            if (o.root_ang_vel && j == 0) st3(o.root_ang_vel + q * 3, p);
+        }
+        if (o.rb_rot || o.root_rot) {
+            Q4 r = slerp(ldg4a(T.grs + (f0 * NB + j) * 4), ldg4a(T.grs + (f1 * NB + j) * 4), blend);
+            if (o.rb_rot) *reinterpret_cast<float4*>(o.rb_rot + (q * NB + j) * 4) = make_float4(r.x, r.y, r.z, r.w);
+            if (o.root_rot && j == 0) st4(o.root_rot + q * 4, r);
+        }
+        if (j >= 1) {
+            if (o.dof_pos) {   // motion_lib.py:605-606, 670-673
+                Q4 r = slerp(ldg4a(T.lrs + (f0 * NB + j) * 4), ldg4a(T.lrs + (f1 * NB + j) * 4), blend);
+                st3(o.dof_pos + q * NDOF + (j - 1) * 3, quat_exp_map(r));
+            }
+            if (o.dof_vel) {
+                V3 p0 = ldg3(T.dvs + (f0 * 23 + (j - 1)) * 3), p1 = ldg3(T.dvs + (f1 * 23 + (j - 1)) * 3);
+                V3 p{lerp(p0.x, p1.x, one_m, blend), lerp(p0.y, p1.y, one_m, blend), lerp(p0.z, p1.z, one_m, blend)};
+                st3(o.dof_vel + q * NDOF + (j - 1) * 3, p);
+            }
+        }
+    }
+    if (o.motion_aa)   // motion_lib.py:619: frame f0 only, not blended
+        for (int c = lane; c < 72; c += 32) o.motion_aa[q * 72 + c] = __ldg(T.motion_aa + f0 * 72 + c);
+    if (o.motion_bodies && lane < 17) o.motion_bodies[q * 17 + lane] = __ldg(T.motion_bodies + id * 17 + lane);
+    if (o.motion_limb_weights && lane < 10) o.motion_limb_weights[q * 10 + lane] = __ldg(T.limb_weights + id * 10 + lane);
+}
+
+__global__ void sample_time_interval_kernel(const float* __restrict__ phase, const float* __restrict__ len, int64_t n,
+                                            int div_mode, float* __restrict__ out) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float fps = (float)(1.0 / 30.0);     // curr_fps = 1/30 as a Python double, cast at the op (motion_lib.py:532)
+    const float x = phase[i] * len[i];
+    const float qv = div_mode ? x * (1.0f / fps) : x / fps;
+    out[i] = (float)(int64_t)qv * fps;
+}
+
+// packed[f] = gts[f] (72) | grs[f] (96) | gvs[f] (72) | gavs[f] (72)
+__global__ void pack_frames_kernel(const phc_motion_tables T, float* __restrict__ packed) {
+    const int64_t total = T.F * FRAME_F;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t f = i / FRAME_F;
+        const int c = (int)(i - f * FRAME_F);
+        float v;
+        if (c < 72) v = __ldg(T.gts + f * 72 + c);
+        else if (c < 168) v = __ldg(T.grs + f * 96 + (c - 72));
+        else if (c < 240) v = __ldg(T.gvs + f * 72 + (c - 168));
+        else v = __ldg(T.gavs + f * 72 + (c - 240));
+        packed[i] = v;
+    }
+}
+
+}  // namespace phc
+
+using namespace phc;
+
+extern "C" int phc_motion_state(const phc_motion_tables* t, const int64_t* motion_ids, const float* motion_times,
+                                const float* offset, int64_t B, const phc_motion_state_out* out, phc_stream_t stream) {
+    PHC_REQUIRE(t && out, PHC_EINVAL, "phc_motion_state: tables/out is NULL");
+    PHC_REQUIRE(B >= 0, PHC_EINVAL, "phc_motion_state: B=%lld < 0", (long long)B);
+    if (B == 0) return PHC_OK;
+    PHC_REQUIRE(motion_ids && motion_times, PHC_EINVAL, "phc_motion_state: motion_ids/motion_times is NULL");
+    PHC_REQUIRE(t->motion_len && t->motion_dt && t->num_frames && t->length_starts, PHC_EINVAL,
+                "phc_motion_state: per-motion tables missing");
+    const phc_motion_state_out& o = *out;
+    PHC_REQUIRE(!(o.rg_pos || o.root_pos) || t->gts, PHC_EINVAL, "phc_motion_state: gts table missing");
+    PHC_REQUIRE(!(o.rb_rot || o.root_rot) || t->grs, PHC_EINVAL, "phc_motion_state: grs table missing");
+    PHC_REQUIRE(!o.dof_pos || t->lrs, PHC_EINVAL, "phc_motion_state: lrs table missing");
+    PHC_REQUIRE(!(o.body_vel || o.root_vel) || t->gvs, PHC_EINVAL, "phc_motion_state: gvs table missing");
+    PHC_REQUIRE(!(o.body_ang_vel || o.root_ang_vel) || t->gavs, PHC_EINVAL, "phc_motion_state: gavs table missing");
+    PHC_REQUIRE(!o.dof_vel || t->dvs, PHC_EINVAL, "phc_motion_state: dvs table missing");
+    PHC_REQUIRE(!o.motion_aa || t->motion_aa, PHC_EINVAL, "phc_motion_state: motion_aa table missing");
+    PHC_REQUIRE(!o.motion_bodies || t->motion_bodies, PHC_EINVAL, "phc_motion_state: motion_bodies table missing");
+    PHC_REQUIRE(!o.motion_limb_weights || t->limb_weights, PHC_EINVAL, "phc_motion_state: limb_weights table missing");
+    PHC_REQUIRE(aligned16(t->grs) && aligned16(t->lrs) && aligned16(o.rb_rot), PHC_EALIGN,
+                "phc_motion_state: grs/lrs tables and rb_rot output must be 16-byte aligned");
+    StateArgs a{*t, motion_ids, motion_times, offset, B, o};
+    const int64_t blocks = (B + MS_WARPS - 1) / MS_WARPS;
+    motion_state_kernel<<<(unsigned)blocks, MS_WARPS * 32, 0, (cudaStream_t)stream>>>(a);
+    return check_launch("phc_motion_state");
+}
+
+extern "C" int phc_sample_time_interval(const float* phase, const float* motion_len, int64_t n, int div_mode, float* out,
+                                        phc_stream_t stream) {
+    PHC_REQUIRE(n >= 0, PHC_EINVAL, "phc_sample_time_interval: n < 0");
+    if (n == 0) return PHC_OK;
+    PHC_REQUIRE(phase && motion_len && out, PHC_EINVAL, "phc_sample_time_interval: NULL pointer");
+    PHC_REQUIRE(div_mode == 0 || div_mode == 1, PHC_EINVAL, "phc_sample_time_interval: div_mode must be 0 or 1");
+    sample_time_interval_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(phase, motion_len, n, div_mode, out);
+    return check_launch("phc_sample_time_interval");
+}
+
+extern "C" int phc_pack_frames(const phc_motion_tables* t, float* packed, phc_stream_t stream) {
+    PHC_REQUIRE(t && packed, PHC_EINVAL, "phc_pack_frames: NULL pointer");
+    PHC_REQUIRE(t->gts && t->grs && t->gvs && t->gavs, PHC_EINVAL, "phc_pack_frames: gts/grs/gvs/gavs required");
+    PHC_REQUIRE(aligned16(packed), PHC_EALIGN, "phc_pack_frames: packed must be 16-byte aligned");
+    if (t->F <= 0) return PHC_OK;
+    const int blocks = sm_count() * 8;
+    pack_frames_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(*t, packed);
+    return check_launch("phc_pack_frames");
+}

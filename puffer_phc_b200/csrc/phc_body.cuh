@@ -1,0 +1,67 @@
+// phc_body.cuh -- per-body pieces of the observation / reward math of reference puffer_phc/envs/common.py,
+// shared by the stand-alone kernels (imitation.cu) and the fused step (step_fused.cu).  The heading
+// quaternion of the simulated root is h = (0, 0, hz, hw) and h^-1 = (0, 0, -hz, hw) (see heading_quat).
+// Host-compilable (tests/host_math_harness.cpp).
+#pragma once
+#include "phc_common.cuh"
+
+namespace phc {
+
+struct BodyState { V3 p; Q4 q; V3 v; V3 w; };   // pos, rot (xyzw), lin vel, ang vel of one body
+
+PHC_HD void put3(float* o, V3 v) { o[0] = v.x; o[1] = v.y; o[2] = v.z; }
+
+// get_motion_state blend of one body (motion_lib.py:596-610); offset is added to the position only.
+PHC_HD BodyState blend_frames(const BodyState& a, const BodyState& b, float blend, V3 off) {
+    const float om = 1.0f - blend;
+    BodyState r;
+    r.p = V3{lerp(a.p.x, b.p.x, om, blend) + off.x, lerp(a.p.y, b.p.y, om, blend) + off.y, lerp(a.p.z, b.p.z, om, blend) + off.z};
+    r.q = slerp(a.q, b.q, blend);
+    r.v = V3{lerp(a.v.x, b.v.x, om, blend), lerp(a.v.y, b.v.y, om, blend), lerp(a.v.z, b.v.z, om, blend)};
+    r.w = V3{lerp(a.w.x, b.w.x, om, blend), lerp(a.w.y, b.w.y, om, blend), lerp(a.w.z, b.w.z, om, blend)};
+    return r;
+}
+
+
+// compute_imitation_observations_v6 for one body (common.py:137-173); b = simulated body, r = reference body.
+PHC_HD void task_obs_body(const BodyState& b, const BodyState& r, V3 root_pos, float hz, float hw, float* o_dpos,
+                          float* o_drot, float* o_dvel, float* o_dang, float* o_lpos, float* o_lrot) {
+    const Q4 hinv{0.0f, 0.0f, -hz, hw}, h{0.0f, 0.0f, hz, hw};
+    put3(o_dpos, rotate_z(-hz, hw, r.p - b.p));                               // :138-139
+    const Q4 dq = quat_mul(r.q, quat_conj(b.q));                              // :142-145
+    tan_norm(quat_mul(quat_mul(hinv, dq), h), o_drot);                        // :146-149, :169
+    put3(o_dvel, rotate_z(-hz, hw, r.v - b.v));                               // :152-153
+    put3(o_dang, rotate_z(-hz, hw, r.w - b.w));                               // :155-156
+    put3(o_lpos, rotate_z(-hz, hw, r.p - root_pos));                          // :159-162
+    tan_norm(quat_mul(hinv, r.q), o_lrot);                                    // :164-165
+}
+
+// compute_humanoid_observations_smpl_max for one body (common.py:57-89). o_pos is written for j >= 1 only.
+PHC_HD void self_obs_body(const BodyState& b, V3 root_pos, float hz, float hw, int j, float* o_pos, float* o_rot,
+                          float* o_vel, float* o_ang) {
+    const Q4 hinv{0.0f, 0.0f, -hz, hw};
+    if (j >= 1) put3(o_pos, rotate_z(-hz, hw, b.p - root_pos));               // :57-66
+    tan_norm(quat_mul(hinv, b.q), o_rot);                                     // :68-75
+    put3(o_vel, rotate_z(-hz, hw, b.v));                                      // :81-83
+    put3(o_ang, rotate_z(-hz, hw, b.w));                                      // :85-89
+}
+
+// compute_imitation_reward, per-body terms (common.py:298-316).
+PHC_HD void reward_terms_body(const BodyState& b, const BodyState& r, float& sp, float& sr, float& sv, float& sa) {
+    sp = mean_sq3(r.p - b.p);
+    const float ang = quat_angle(quat_mul(r.q, quat_conj(b.q)));
+    sr = ang * ang;
+    sv = mean_sq3(r.v - b.v);
+    sa = mean_sq3(r.w - b.w);
+}
+
+// compute_imitation_reward, env-level tail (common.py:300-320): means over J, exp kernels, weighted sum.
+PHC_HD float reward_from_sums(float sp, float sr, float sv, float sa, float J, const float* k, const float* w, float* raw) {
+    raw[0] = expf(-k[0] * (sp / J));
+    raw[1] = expf(-k[1] * (sr / J));
+    raw[2] = expf(-k[2] * (sv / J));
+    raw[3] = expf(-k[3] * (sa / J));
+    return ((w[0] * raw[0] + w[1] * raw[1]) + w[2] * raw[2]) + w[3] * raw[3];
+}
+
+}  // namespace phc

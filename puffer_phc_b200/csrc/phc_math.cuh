@@ -1,0 +1,166 @@
+// phc_math.cuh -- fp32 quaternion / heading / frame-blend math of the PHC hot path.
+//
+// Every function mirrors the *operation order* of the reference's torch code (one rounding per
+// torch op, no FMA contraction) so that integer results and branch decisions are reproducible
+// bit for bit and floating-point results stay within 1e-5 of the reference.  The translation
+// unit that includes this header MUST be compiled with -fmad=false (nvcc) / -ffp-contract=off
+// (host harness); explicit fmaf() is used only where the reference's CPU kernel fuses.
+// Quaternions are xyzw (reference puffer_phc/torch_utils.py:61-62).
+//
+// The header compiles for the host as well (tests/host_math_harness.cpp) so the math can be
+// checked on a CPU-only box before it ever runs on the GPU.
+#pragma once
+#include <math.h>
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define PHC_HD __host__ __device__ __forceinline__
+#else
+#define PHC_HD inline
+#endif
+
+namespace phc {
+
+struct V3 { float x, y, z; };
+struct Q4 { float x, y, z, w; };
+
+PHC_HD V3 operator-(V3 a, V3 b) { return V3{a.x - b.x, a.y - b.y, a.z - b.z}; }
+
+// torch.clip(x, 0, 1): NaN propagates (fminf/fmaxf would drop it).
+PHC_HD float clip01(float x) {
+    if (x != x) return x;
+    return x < 0.0f ? 0.0f : (x > 1.0f ? 1.0f : x);
+}
+
+// MotionLibBase._calc_frame_blend (reference puffer_phc/motion_lib.py:655-665).
+// phase uses the un-clamped time; only the lower clamp is applied to time afterwards.
+PHC_HD void frame_blend(float time, float len, int64_t nf, float dt, int64_t& idx0, int64_t& idx1, float& blend) {
+    float phase = clip01(time / len);
+    if (time < 0.0f) time = 0.0f;
+    idx0 = (int64_t)(phase * (float)(nf - 1));
+    idx1 = idx0 + 1 < nf - 1 ? idx0 + 1 : nf - 1;
+    blend = clip01((time - (float)idx0 * dt) / dt);
+}
+
+// quat_mul (torch_utils.py:55-75): the 8-multiply form, expression order kept.
+PHC_HD Q4 quat_mul(Q4 a, Q4 b) {
+    float ww = (a.z + a.x) * (b.x + b.y);
+    float yy = (a.w - a.y) * (b.w + b.z);
+    float zz = (a.w + a.y) * (b.w - b.z);
+    float xx = (ww + yy) + zz;
+    float qq = 0.5f * (xx + (a.z - a.x) * (b.x - b.y));
+    Q4 r;
+    r.w = (qq - ww) + (a.z - a.y) * (b.y - b.z);
+    r.x = (qq - xx) + (a.x + a.w) * (b.x + b.w);
+    r.y = (qq - yy) + (a.w - a.x) * (b.y + b.z);
+    r.z = (qq - zz) + (a.z + a.y) * (b.w - b.x);
+    return r;
+}
+
+// quat_conjugate (torch_utils.py:79-82)
+PHC_HD Q4 quat_conj(Q4 a) { return Q4{-a.x, -a.y, -a.z, a.w}; }
+
+// my_quat_rotate (torch_utils.py:274-281): v*(2w^2-1) + cross(q,v)*w*2 + q*dot(q,v)*2
+PHC_HD V3 quat_rotate(Q4 q, V3 v) {
+    float s = 2.0f * (q.w * q.w) - 1.0f;
+    float cx = q.y * v.z - q.z * v.y, cy = q.z * v.x - q.x * v.z, cz = q.x * v.y - q.y * v.x;
+    float d = (q.x * v.x + q.y * v.y) + q.z * v.z;
+    V3 r;
+    r.x = (v.x * s + (cx * q.w) * 2.0f) + (q.x * d) * 2.0f;
+    r.y = (v.y * s + (cy * q.w) * 2.0f) + (q.y * d) * 2.0f;
+    r.z = (v.z * s + (cz * q.w) * 2.0f) + (q.z * d) * 2.0f;
+    return r;
+}
+
+// my_quat_rotate for a pure z-rotation q = (0, 0, qz, qw) (the heading quaternions): the terms that
+// multiply the zero components are dropped; x+0 and 0*x are exact so the result is unchanged.
+PHC_HD V3 rotate_z(float qz, float qw, V3 v) {
+    float s = 2.0f * (qw * qw) - 1.0f;
+    float cx = -(qz * v.y), cy = qz * v.x;
+    float d = qz * v.z;
+    V3 r;
+    r.x = v.x * s + (cx * qw) * 2.0f;
+    r.y = v.y * s + (cy * qw) * 2.0f;
+    r.z = v.z * s + (qz * d) * 2.0f;
+    return r;
+}
+
+// quat_to_tan_norm (torch_utils.py:285-297): my_quat_rotate of (1,0,0) then (0,0,1); zero terms dropped.
+PHC_HD void tan_norm(Q4 q, float* o) {
+    float s = 2.0f * (q.w * q.w) - 1.0f;
+    o[0] = s + (q.x * q.x) * 2.0f;
+    o[1] = (q.z * q.w) * 2.0f + (q.y * q.x) * 2.0f;
+    o[2] = ((-q.y) * q.w) * 2.0f + (q.z * q.x) * 2.0f;
+    o[3] = (q.y * q.w) * 2.0f + (q.x * q.z) * 2.0f;
+    o[4] = ((-q.x) * q.w) * 2.0f + (q.y * q.z) * 2.0f;
+    o[5] = s + (q.z * q.z) * 2.0f;
+}
+
+// calc_heading (torch_utils.py:369-380): atan2 of the rotated x axis.
+PHC_HD float calc_heading(Q4 q) {
+    float s = 2.0f * (q.w * q.w) - 1.0f;
+    float dx = s + (q.x * q.x) * 2.0f;
+    float dy = (q.z * q.w) * 2.0f + (q.y * q.x) * 2.0f;
+    return atan2f(dy, dx);
+}
+
+// calc_heading_quat (torch_utils.py:384-394) = quat_from_angle_axis(heading, z) (:354-358):
+// (0, 0, sin(h/2), cos(h/2)) divided by its norm (quat_unit :174-179; torch's CPU norm
+// accumulates squares with an fma chain).  calc_heading_quat_inv (:398-408) uses -heading,
+// i.e. exactly the conjugate, because sin is odd and cos even in every libm used here.
+PHC_HD void heading_quat(float heading, float& qz, float& qw) {
+    float th = heading / 2.0f;
+    float sn = sinf(th), cs = cosf(th);
+    float n = sqrtf(fmaf(cs, cs, sn * sn));
+    if (n < 1e-9f) n = 1e-9f;
+    qz = sn / n;
+    qw = cs / n;
+}
+
+// remove_base_rot (reference puffer_phc/envs/common.py:15-19), used when upright == false.
+PHC_HD Q4 remove_base_rot(Q4 q) { return quat_mul(q, Q4{-0.5f, -0.5f, -0.5f, 0.5f}); }
+
+// quat_to_angle_axis (torch_utils.py:86-106) -> angle only (normalize_angle :50-51 applied).
+PHC_HD float quat_angle(Q4 q) {
+    float s = sqrtf(1.0f - q.w * q.w);
+    if (!(fabsf(s) > 1e-5f)) return 0.0f;      // NaN -> masked, like torch.where on a false mask
+    float a = 2.0f * acosf(q.w);
+    return atan2f(sinf(a), cosf(a));
+}
+
+// quat_to_exp_map (torch_utils.py:144-150)
+PHC_HD V3 quat_exp_map(Q4 q) {
+    float s = sqrtf(1.0f - q.w * q.w);
+    if (!(fabsf(s) > 1e-5f)) return V3{0.0f, 0.0f, 0.0f};     // angle 0 times axis (0,0,1)
+    float a = 2.0f * acosf(q.w);
+    a = atan2f(sinf(a), cosf(a));
+    return V3{a * (q.x / s), a * (q.y / s), a * (q.z / s)};
+}
+
+// slerp (torch_utils.py:110-131).  The two torch.where fall-backs are evaluated first (they
+// discard the trigonometric result anyway): q0 when |cos| >= 1, the un-normalised midpoint when
+// |sin| < 1e-3.  No renormalisation.
+PHC_HD Q4 slerp(Q4 q0, Q4 q1, float t) {
+    float c = ((q0.x * q1.x + q0.y * q1.y) + q0.z * q1.z) + q0.w * q1.w;
+    if (c < 0.0f) { q1.x = -q1.x; q1.y = -q1.y; q1.z = -q1.z; q1.w = -q1.w; }
+    c = fabsf(c);
+    if (c >= 1.0f) return q0;
+    float s = sqrtf(1.0f - c * c);
+    if (fabsf(s) < 0.001f)
+        return Q4{0.5f * q0.x + 0.5f * q1.x, 0.5f * q0.y + 0.5f * q1.y, 0.5f * q0.z + 0.5f * q1.z, 0.5f * q0.w + 0.5f * q1.w};
+    float h = acosf(c);
+    float ra = sinf((1.0f - t) * h) / s;
+    float rb = sinf(t * h) / s;
+    return Q4{ra * q0.x + rb * q1.x, ra * q0.y + rb * q1.y, ra * q0.z + rb * q1.z, ra * q0.w + rb * q1.w};
+}
+
+// lerp as written in get_motion_state (motion_lib.py:596-603): (1-b)*x0 + b*x1
+PHC_HD float lerp(float a, float b, float one_m, float t) { return one_m * a + t * b; }
+
+// torch.norm over 3 components on the CPU reference: sqrt(fma(z,z,fma(y,y,x*x))).
+PHC_HD float norm3(V3 d) { return sqrtf(fmaf(d.z, d.z, fmaf(d.y, d.y, d.x * d.x))); }
+
+// mean over xyz of squares: ((x^2 + y^2) + z^2) / 3  ((diff**2).mean(dim=-1), common.py:300)
+PHC_HD float mean_sq3(V3 d) { return ((d.x * d.x + d.y * d.y) + d.z * d.z) / 3.0f; }
+
+}  // namespace phc

@@ -1,0 +1,174 @@
+// rms.cu -- RunningNorm (reference puffer_phc/policies/running_norm.py:5-53).
+//   forward  (:15-20)  y = clamp((x - mean) / sqrt(var + eps), -clip, clip)
+//   update   (:23-34)  split into   moments (per-column sum / sum of squares, fp64, deterministic)
+//                                   [all-reduce across ranks happens here, on the moments buffer]
+//                                   finalize (batch mean / biased var -> running average, count += 1)
+// Memory-bound column pass: thread = column (coalesced rows), 4 independent rows in flight per thread.
+#include "phc_common.cuh"
+
+namespace phc {
+
+constexpr int RMS_THREADS = 256;
+
+__device__ __forceinline__ float norm_clamp(float x, float mean, float den, float clip) {
+    float y = (x - mean) / den;
+    return (y != y) ? y : fminf(fmaxf(y, -clip), clip);     // torch.clamp propagates NaN
+}
+
+// contiguous [B*C] fast path: float4 in, float4 out.
+__global__ void __launch_bounds__(RMS_THREADS) rms_forward_vec_kernel(const float4* __restrict__ x, const float* __restrict__ mean,
+                                                                      const float* __restrict__ var, float eps, float clip,
+                                                                      int64_t n4, int C, float4* __restrict__ y) {
+    extern __shared__ float sm[];
+    float* s_mean = sm;
+    float* s_den = sm + C;
+    for (int c = threadIdx.x; c < C; c += blockDim.x) { s_mean[c] = __ldg(mean + c); s_den[c] = sqrtf(__ldg(var + c) + eps); }
+    __syncthreads();
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+        float4 v = __ldg(x + i);
+        int c = (int)((i << 2) % C);
+        float r[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            r[u] = norm_clamp(r[u], s_mean[c], s_den[c], clip);
+            c = (c + 1 == C) ? 0 : c + 1;
+        }
+        y[i] = make_float4(r[0], r[1], r[2], r[3]);
+    }
+}
+
+// generic strided rows.
+__global__ void __launch_bounds__(RMS_THREADS) rms_forward_kernel(const float* __restrict__ x, int64_t xs, const float* __restrict__ mean,
+                                                                  const float* __restrict__ var, float eps, float clip, int64_t B,
+                                                                  int C, float* __restrict__ y, int64_t ys) {
+    extern __shared__ float sm[];
+    float* s_mean = sm;
+    float* s_den = sm + C;
+    for (int c = threadIdx.x; c < C; c += blockDim.x) { s_mean[c] = __ldg(mean + c); s_den[c] = sqrtf(__ldg(var + c) + eps); }
+    __syncthreads();
+    for (int64_t b = blockIdx.x; b < B; b += gridDim.x)
+        for (int c = threadIdx.x; c < C; c += blockDim.x) y[b * ys + c] = norm_clamp(__ldg(x + b * xs + c), s_mean[c], s_den[c], clip);
+}
+
+// partial[blockIdx.x][0][c] = sum over this block's rows of x[:,c]; [1][c] = sum of squares.  blockIdx.y = column chunk.
+__global__ void __launch_bounds__(RMS_THREADS) rms_moments_kernel(const float* __restrict__ x, int64_t xs, int64_t B, int C,
+                                                                  int64_t rows_per_block, double* __restrict__ partial) {
+    const int c = blockIdx.y * RMS_THREADS + threadIdx.x;
+    if (c >= C) return;
+    const int64_t r0 = (int64_t)blockIdx.x * rows_per_block;
+    const int64_t r1 = (r0 + rows_per_block < B) ? r0 + rows_per_block : B;
+    double s = 0.0, q = 0.0;
+    int64_t r = r0;
+    for (; r + 4 <= r1; r += 4) {
+        const float a0 = __ldg(x + (r + 0) * xs + c), a1 = __ldg(x + (r + 1) * xs + c);
+        const float a2 = __ldg(x + (r + 2) * xs + c), a3 = __ldg(x + (r + 3) * xs + c);
+        const double d0 = a0, d1 = a1, d2 = a2, d3 = a3;
+        s += d0; q += d0 * d0; s += d1; q += d1 * d1; s += d2; q += d2 * d2; s += d3; q += d3 * d3;
+    }
+    for (; r < r1; ++r) { const double d = __ldg(x + r * xs + c); s += d; q += d * d; }
+    double* p = partial + (int64_t)blockIdx.x * 2 * C;
+    p[c] = s;
+    p[C + c] = q;
+}
+
+// moments[1 + i] += sum_p partial[p][i] for i in [0, 2C), fixed order; moments[0] += rows.
+__global__ void rms_reduce_kernel(const double* __restrict__ partial, int P, int64_t rows, int C, double* __restrict__ moments) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < 2 * C) {
+        double s = 0.0;
+        for (int p = 0; p < P; ++p) s += partial[(int64_t)p * 2 * C + i];
+        moments[1 + i] += s;
+    }
+    if (i == 0) moments[0] += (double)rows;
+}
+
+// running_norm.py:26-34 on the accumulated moments; a single block so that count is read before it is bumped.
+__global__ void rms_finalize_kernel(const double* __restrict__ moments, int C, float* __restrict__ running_mean,
+                                    float* __restrict__ running_var, float* __restrict__ count) {
+    const double n = moments[0];
+    const float weight = 1.0f / count[0];
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        const double m = moments[1 + c] / n;
+        double v = moments[1 + C + c] / n - m * m;          // biased variance (unbiased=False)
+        if (v < 0.0) v = 0.0;
+        const float mean_b = (float)m, var_b = (float)v;
+        running_mean[c] = running_mean[c] * (1.0f - weight) + mean_b * weight;
+        running_var[c] = running_var[c] * (1.0f - weight) + var_b * weight;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) count[0] = count[0] + 1.0f;
+}
+
+static int moments_row_blocks() { return 4 * sm_count(); }
+
+}  // namespace phc
+
+using namespace phc;
+
+extern "C" int phc_rms_forward(const float* x, int64_t x_stride, const float* mean, const float* var, float eps, float clip,
+                               int64_t B, int C, float* y, int64_t y_stride, phc_stream_t stream) {
+    const char* fn = "phc_rms_forward";
+    PHC_REQUIRE(B >= 0, PHC_EINVAL, "%s: B < 0", fn);
+    PHC_REQUIRE(C >= 1 && C <= 6000, PHC_ESHAPE, "%s: C=%d outside [1,6000]", fn, C);
+    if (B == 0) return PHC_OK;
+    PHC_REQUIRE(x && mean && var && y, PHC_EINVAL, "%s: NULL pointer", fn);
+    PHC_REQUIRE(x_stride >= C && y_stride >= C, PHC_ESHAPE, "%s: row stride < C", fn);
+    cudaStream_t s = (cudaStream_t)stream;
+    const size_t smem = 2 * (size_t)C * sizeof(float);
+    const int64_t total = B * C;
+    if (x_stride == C && y_stride == C && (total & 3) == 0 && aligned16(x) && aligned16(y)) {
+        const int64_t n4 = total >> 2;
+        int64_t blocks = (n4 + RMS_THREADS - 1) / RMS_THREADS;
+        const int64_t cap = (int64_t)sm_count() * 8;
+        if (blocks > cap) blocks = cap;
+        rms_forward_vec_kernel<<<(unsigned)blocks, RMS_THREADS, smem, s>>>(reinterpret_cast<const float4*>(x), mean, var, eps, clip, n4,
+                                                                          C, reinterpret_cast<float4*>(y));
+    } else {
+        int64_t blocks = B;
+        const int64_t cap = (int64_t)sm_count() * 8;
+        if (blocks > cap) blocks = cap;
+        rms_forward_kernel<<<(unsigned)blocks, RMS_THREADS, smem, s>>>(x, x_stride, mean, var, eps, clip, B, C, y, y_stride);
+    }
+    return check_launch(fn);
+}
+
+extern "C" int64_t phc_rms_scratch_doubles(int C) { return C < 1 ? 0 : (int64_t)moments_row_blocks() * 2 * C; }
+
+extern "C" int phc_rms_moments(const float* x, int64_t x_stride, int64_t B, int C, double* moments, double* scratch,
+                               phc_stream_t stream) {
+    const char* fn = "phc_rms_moments";
+    PHC_REQUIRE(B >= 0, PHC_EINVAL, "%s: B < 0", fn);
+    PHC_REQUIRE(C >= 1, PHC_ESHAPE, "%s: C < 1", fn);
+    if (B == 0) return PHC_OK;
+    PHC_REQUIRE(x && moments && scratch, PHC_EINVAL, "%s: NULL pointer", fn);
+    PHC_REQUIRE(x_stride >= C, PHC_ESHAPE, "%s: row stride < C", fn);
+    cudaStream_t s = (cudaStream_t)stream;
+    int64_t row_blocks = (B + 63) / 64;
+    if (row_blocks > moments_row_blocks()) row_blocks = moments_row_blocks();
+    const int64_t rows_per_block = (B + row_blocks - 1) / row_blocks;
+    row_blocks = (B + rows_per_block - 1) / rows_per_block;
+    dim3 grid((unsigned)row_blocks, (unsigned)((C + RMS_THREADS - 1) / RMS_THREADS));
+    rms_moments_kernel<<<grid, RMS_THREADS, 0, s>>>(x, x_stride, B, C, rows_per_block, scratch);
+    int rc = check_launch(fn);
+    if (rc) return rc;
+    rms_reduce_kernel<<<(2 * C + 255) / 256, 256, 0, s>>>(scratch, (int)row_blocks, B, C, moments);
+    return check_launch(fn);
+}
+
+extern "C" int phc_rms_reduce_partials(const double* partials, int num_partials, int64_t rows, int C, double* moments,
+                                       phc_stream_t stream) {
+    const char* fn = "phc_rms_reduce_partials";
+    PHC_REQUIRE(partials && moments, PHC_EINVAL, "%s: NULL pointer", fn);
+    PHC_REQUIRE(num_partials >= 0 && rows >= 0 && C >= 1, PHC_EINVAL, "%s: bad size", fn);
+    rms_reduce_kernel<<<(2 * C + 255) / 256, 256, 0, (cudaStream_t)stream>>>(partials, num_partials, rows, C, moments);
+    return check_launch(fn);
+}
+
+extern "C" int phc_rms_finalize(const double* moments, int C, float* running_mean, float* running_var, float* count,
+                                phc_stream_t stream) {
+    const char* fn = "phc_rms_finalize";
+    PHC_REQUIRE(moments && running_mean && running_var && count, PHC_EINVAL, "%s: NULL pointer", fn);
+    PHC_REQUIRE(C >= 1, PHC_ESHAPE, "%s: C < 1", fn);
+    rms_finalize_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(moments, C, running_mean, running_var, count);
+    return check_launch(fn);
+}

@@ -1,0 +1,101 @@
+"""Drop-ins for the four hot free functions of the reference's ``puffer_phc/envs/common.py``: same names,
+positional arguments, return shapes/dtypes.  Inputs may be strided views of the PhysX rigid-body buffer
+(``state[..., :24, 0:3]``, reference puffer_phc/envs/humanoid_phc.py:546-549) -- they are consumed in place
+through ``phc_view`` (base pointer + env/body strides); only tensors whose innermost stride is not 1 are
+copied.  Kernels: csrc/imitation.cu.  CUDA tensors only; there is no CPU implementation here.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, Tuple
+
+import torch
+
+from .. import _ffi
+
+_KEYS_K = ("k_pos", "k_rot", "k_vel", "k_ang_vel")
+_KEYS_W = ("w_pos", "w_rot", "w_vel", "w_ang_vel")
+
+
+def _prep(*ts):
+    _ffi.require_cuda(*ts)
+    return [_ffi.as_view_tensor(t) for t in ts]
+
+
+def compute_imitation_observations_v6(root_pos, root_rot, body_pos, body_rot, body_vel, body_ang_vel, ref_body_pos,
+                                      ref_body_rot, ref_body_vel, ref_body_ang_vel, time_steps: int, upright: bool):
+    """reference envs/common.py:106-176 -> ``[B, J*24]`` (six body-major blocks 3J|6J|3J|3J|3J|6J)."""
+    lib = _ffi.load()
+    ts = _prep(root_pos, root_rot, body_pos, body_rot, body_vel, body_ang_vel, ref_body_pos, ref_body_rot, ref_body_vel,
+               ref_body_ang_vel)
+    B, J = ts[2].shape[0], ts[2].shape[1]
+    obs = torch.empty((B, 24 * J), dtype=torch.float32, device=ts[2].device)
+    with torch.cuda.device(obs.device):
+        _ffi.check(lib.phc_imitation_obs_v6(*[_ffi.view3(t) for t in ts], B, J, int(time_steps), int(bool(upright)),
+                                            _ffi.ptr(obs), obs.stride(0), _ffi.stream_ptr()), "compute_imitation_observations_v6")
+    return obs
+
+
+def compute_humanoid_observations_smpl_max(body_pos, body_rot, body_vel, body_ang_vel, smpl_params, limb_weight_params,
+                                           local_root_obs, root_height_obs, upright, has_smpl_params, has_limb_weight_params):
+    """reference envs/common.py:23-103 -> ``[B, (1) + 3(J-1) + 12J (+ params)]``."""
+    lib = _ffi.load()
+    ts = _prep(body_pos, body_rot, body_vel, body_ang_vel)
+    B, J = ts[0].shape[0], ts[0].shape[1]
+    W = (1 if root_height_obs else 0) + 3 * (J - 1) + 12 * J
+    extra = []
+    if has_smpl_params:            # plain pass-through columns (common.py:96-100)
+        extra.append(smpl_params)
+    if has_limb_weight_params:
+        extra.append(limb_weight_params)
+    Wt = W + sum(int(x.shape[-1]) for x in extra)
+    obs = torch.empty((B, Wt), dtype=torch.float32, device=ts[0].device)
+    with torch.cuda.device(obs.device):
+        _ffi.check(lib.phc_self_obs_smpl_max(*[_ffi.view3(t) for t in ts], B, J, int(bool(local_root_obs)),
+                                             int(bool(root_height_obs)), int(bool(upright)), _ffi.ptr(obs), obs.stride(0),
+                                             _ffi.stream_ptr()), "compute_humanoid_observations_smpl_max")
+    col = W
+    for x in extra:
+        obs[:, col:col + x.shape[-1]] = x
+        col += x.shape[-1]
+    return obs
+
+
+def compute_imitation_reward(root_pos, root_rot, body_pos, body_rot, body_vel, body_ang_vel, ref_body_pos, ref_body_rot,
+                             ref_body_vel, ref_body_ang_vel, rwd_specs: Dict[str, float]) -> Tuple[torch.Tensor, torch.Tensor]:
+    """reference envs/common.py:270-322 -> ``(reward [B], reward_raw [B,4])``.  root_pos/root_rot are unused there too."""
+    lib = _ffi.load()
+    ts = _prep(body_pos, body_rot, body_vel, body_ang_vel, ref_body_pos, ref_body_rot, ref_body_vel, ref_body_ang_vel)
+    B, J = ts[0].shape[0], ts[0].shape[1]
+    k = (C.c_float * 4)(*[float(rwd_specs[n]) for n in _KEYS_K])
+    w = (C.c_float * 4)(*[float(rwd_specs[n]) for n in _KEYS_W])
+    reward = torch.empty(B, dtype=torch.float32, device=ts[0].device)
+    raw = torch.empty((B, 4), dtype=torch.float32, device=ts[0].device)
+    with torch.cuda.device(reward.device):
+        _ffi.check(lib.phc_imitation_reward(*[_ffi.view3(t) for t in ts], B, J, k, w, _ffi.ptr(reward), _ffi.ptr(raw), 4,
+                                            _ffi.stream_ptr()), "compute_imitation_reward")
+    return reward, raw
+
+
+def compute_humanoid_im_reset(reset_buf, progress_buf, contact_buf, contact_body_ids, rigid_body_pos, ref_body_pos, pass_time,
+                              enable_early_termination, termination_distance, use_mean):
+    """reference envs/common.py:325-364 -> ``(reset, terminated)`` with reset_buf's dtype.  contact_buf and
+    contact_body_ids are unused by the reference as well."""
+    lib = _ffi.load()
+    pos, ref = _prep(rigid_body_pos, ref_body_pos)
+    _ffi.require_cuda(progress_buf, pass_time, termination_distance)
+    B, J = pos.shape[0], pos.shape[1]
+    prog = progress_buf.to(torch.int16).contiguous()
+    pt = pass_time.to(torch.bool).contiguous()
+    td = termination_distance.to(torch.float32).reshape(-1).contiguous()
+    if td.numel() == 1 and J > 1:
+        td = td.expand(J).contiguous()
+    reset = torch.empty(B, dtype=torch.bool, device=pos.device)
+    term = torch.empty(B, dtype=torch.bool, device=pos.device)
+    with torch.cuda.device(pos.device):
+        _ffi.check(lib.phc_im_reset(_ffi.ptr(prog), _ffi.view3(pos), _ffi.view3(ref), _ffi.ptr(pt), int(bool(enable_early_termination)),
+                                    _ffi.ptr(td), int(bool(use_mean)), B, J, _ffi.ptr(reset), _ffi.ptr(term), _ffi.stream_ptr()),
+                   "compute_humanoid_im_reset")
+    if reset_buf.dtype != torch.bool:
+        reset, term = reset.to(reset_buf.dtype), term.to(reset_buf.dtype)
+    return reset, term

@@ -1,0 +1,167 @@
+"""The whole post-physics half of ``HumanoidPHC.step`` as ONE kernel launch.
+
+Reference flow (puffer_phc/envs/humanoid_phc.py:136-149): ``_compute_reward`` (:1228-1303) ->
+``_compute_reset`` (:1311-1333) -> ``_compute_observations`` (:935-959), with two ``get_motion_state`` queries
+(t and t+1) behind them and ``RunningNorm.forward`` applied later by the policy.  ``FusedStep`` takes the same
+per-env buffers the env holds (PhysX rigid-body tensor, ``progress_buf``, ``_motion_start_times``,
+``_motion_start_times_offset``, ``_sampled_motion_ids``, ``_global_offset``, ``dof_force_tensor``, ``_dof_vel``)
+and fills ``obs_buf``, ``rew_buf``, ``reward_raw``, ``reset_buf``, ``_terminate_buf`` -- optionally also the
+RMS-normalised observation and the fp64 column moments ``RunningNorm.update`` needs -- in one pass over HBM
+(csrc/step_fused.cu).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass, field
+from typing import Dict, Optional, Sequence
+
+import torch
+
+from . import _ffi
+from .motion_lib import MotionLibBase
+from .policies.running_norm import RunningNorm
+
+NUM_BODIES, OBS_DIM = 24, 934
+EVAL_BODY_IDS = tuple(j for j in range(24) if j not in (4, 8, 18, 23))   # body_sets.py:42,57
+
+
+@dataclass
+class StepConfig:
+    """Kernel constants; defaults = the reference's config.py defaults."""
+    dt: float = 1.0 / 30.0                      # isaacgym_env.py:39-41
+    k_pos: float = 100.0                        # RewardConfig, config.py:25-32
+    k_rot: float = 10.0
+    k_vel: float = 0.1
+    k_ang_vel: float = 0.1
+    w_pos: float = 0.5
+    w_rot: float = 0.3
+    w_vel: float = 0.1
+    w_ang_vel: float = 0.1
+    use_power_reward: bool = True               # config.py:37
+    rew_power_coef: float = 0.0005              # config.py:96
+    enable_early_termination: bool = True       # config.py:84
+    termination_distance: float = 0.25          # config.py:85
+    reset_bodies: Sequence[int] = field(default_factory=lambda: tuple(range(24)))
+    use_mean: bool = False                      # flag_im_eval (humanoid_phc.py:1332)
+
+    def eval_mode(self) -> "StepConfig":
+        """toggle_eval_mode (humanoid_phc.py:1421-1438): 0.5 m, mean over the 20 eval bodies."""
+        import dataclasses
+        return dataclasses.replace(self, termination_distance=0.5, reset_bodies=EVAL_BODY_IDS, use_mean=True)
+
+
+class FusedStep:
+    def __init__(self, motion_lib: MotionLibBase, num_envs: int, cfg: Optional[StepConfig] = None,
+                 rms: Optional[RunningNorm] = None, normalize: bool = False, accumulate_moments: bool = False,
+                 debug_ref: bool = False):
+        self.lib = _ffi.load()
+        self.motion_lib = motion_lib
+        self.cfg = cfg or StepConfig()
+        self.N = int(num_envs)
+        dev = motion_lib._device
+        self.device = dev
+        self.rms = rms
+        self.normalize = bool(normalize)
+        self.accumulate_moments = bool(accumulate_moments)
+        if (normalize or accumulate_moments) and rms is None:
+            raise ValueError("normalize / accumulate_moments need a RunningNorm")
+        c = self.cfg
+        self.raw_dim = 5 if c.use_power_reward else 4
+        # the env's output buffers (humanoid_phc.py:554-575)
+        self.obs_buf = torch.zeros((self.N, OBS_DIM), dtype=torch.float32, device=dev)
+        self.obs_norm = torch.zeros((self.N, OBS_DIM), dtype=torch.float32, device=dev) if normalize else None
+        self.rew_buf = torch.zeros(self.N, dtype=torch.float32, device=dev)
+        self.reward_raw = torch.zeros((self.N, self.raw_dim), dtype=torch.float32, device=dev)
+        self.reset_buf = torch.ones(self.N, dtype=torch.bool, device=dev)
+        self.terminate_buf = torch.ones(self.N, dtype=torch.bool, device=dev)
+        self.termination_distances = torch.full((NUM_BODIES,), float(c.termination_distance), dtype=torch.float32, device=dev)
+        self.num_partials = int(self.lib.phc_step_num_partials())
+        self.partials = (torch.zeros((self.num_partials, 2, OBS_DIM), dtype=torch.float64, device=dev)
+                         if accumulate_moments else None)
+        self.ref_t = torch.zeros((self.N, 312), dtype=torch.float32, device=dev) if debug_ref else None
+        self.ref_t1 = torch.zeros((self.N, 312), dtype=torch.float32, device=dev) if debug_ref else None
+        mask = 0
+        for j in c.reset_bodies:
+            mask |= 1 << int(j)
+        self._ccfg = _ffi.StepCfg(
+            float(torch.tensor(c.dt, dtype=torch.float32)),
+            (C.c_float * 4)(c.k_pos, c.k_rot, c.k_vel, c.k_ang_vel), (C.c_float * 4)(c.w_pos, c.w_rot, c.w_vel, c.w_ang_vel),
+            float(c.rew_power_coef), mask, int(c.enable_early_termination), int(c.use_mean),
+            float(rms.epsilon) if rms is not None else 1e-5, float(rms.clip) if rms is not None else 10.0)
+
+    def set_termination_distances(self, d) -> None:           # humanoid_phc.py:1336-1337
+        self.termination_distances[:] = d
+
+    def __call__(self, body_state, progress_buf, motion_start_times, motion_start_times_offset, sampled_motion_ids,
+                 global_offset, dof_force=None, dof_vel=None, out: Optional[Dict[str, torch.Tensor]] = None) -> Dict[str, torch.Tensor]:
+        """Run the step.  ``body_state`` is the PhysX rigid-body tensor ``[N, bodies_per_env, 13]`` (or ``[N, S]``);
+        returns the dict of output buffers (owned by this object unless ``out`` supplies them)."""
+        _ffi.require_cuda(body_state, progress_buf, motion_start_times, motion_start_times_offset, sampled_motion_ids, global_offset)
+        N = self.N
+        for name, t, dt in (("progress_buf", progress_buf, torch.int16), ("motion_start_times", motion_start_times, torch.float32),
+                            ("motion_start_times_offset", motion_start_times_offset, torch.float32),
+                            ("sampled_motion_ids", sampled_motion_ids, torch.int64), ("global_offset", global_offset, torch.float32),
+                            ("dof_force", dof_force, torch.float32), ("dof_vel", dof_vel, torch.float32)):
+            if t is None:
+                continue
+            if t.dtype != dt or not t.is_contiguous() or t.shape[0] != N:
+                raise TypeError(f"{name}: expected a contiguous {dt} tensor with {N} rows (as the reference env holds it), "
+                                f"got {t.dtype} {tuple(t.shape)} contiguous={t.is_contiguous()}")
+        bs = body_state.reshape(N, -1)
+        if bs.dtype != torch.float32 or bs.stride(1) != 1:
+            bs = bs.float().contiguous()
+        use_power = self.cfg.use_power_reward
+        if use_power and (dof_force is None or dof_vel is None):
+            raise ValueError("use_power_reward=True needs dof_force and dof_vel")
+        o = out or {}
+        obs = o.get("obs", self.obs_buf)
+        obs_norm = o.get("obs_norm", self.obs_norm)
+        rew, raw = o.get("reward", self.rew_buf), o.get("reward_raw", self.reward_raw)
+        reset, term = o.get("reset", self.reset_buf), o.get("terminated", self.terminate_buf)
+        sin = _ffi.StepIn(
+            bs.data_ptr(), bs.stride(0), progress_buf.data_ptr(), motion_start_times.data_ptr(), motion_start_times_offset.data_ptr(),
+            sampled_motion_ids.data_ptr(), global_offset.data_ptr(),
+            dof_force.data_ptr() if use_power else None, dof_vel.data_ptr() if use_power else None,
+            self.termination_distances.data_ptr(),
+            self.rms.running_mean.data_ptr() if self.normalize else None, self.rms.running_var.data_ptr() if self.normalize else None, N)
+        sout = _ffi.StepOut(
+            obs.data_ptr(), obs.stride(0), obs_norm.data_ptr() if self.normalize else None, rew.data_ptr(), raw.data_ptr(),
+            raw.stride(0), reset.data_ptr(), term.data_ptr(), self.partials.data_ptr() if self.accumulate_moments else None,
+            self.ref_t.data_ptr() if self.ref_t is not None else None, self.ref_t1.data_ptr() if self.ref_t1 is not None else None)
+        with torch.cuda.device(self.device):
+            _ffi.check(self.lib.phc_step_fused(C.byref(self.motion_lib.ctables), C.byref(sin), C.byref(self._ccfg), C.byref(sout),
+                                               _ffi.stream_ptr()), "phc_step_fused")
+            if self.accumulate_moments:
+                self.rms.accumulate_partials(self.partials, N)
+        res = {"obs": obs, "reward": rew, "reward_raw": raw, "reset": reset, "terminated": term}
+        if self.normalize:
+            res["obs_norm"] = obs_norm
+        return res
+
+    # ---- host-buffer entry (end-to-end path): H2D of the per-env inputs, the kernel, D2H of reward / flags ------------
+    _HOST_KEYS = ("body_state", "progress", "start_time", "start_offset", "motion_ids", "global_offset", "dof_force", "dof_vel")
+
+    def step_host(self, host: Dict[str, torch.Tensor]) -> Dict[str, torch.Tensor]:
+        """Same step with HOST (ideally pinned) input tensors, as a simulator living on the host would hand them over.
+        Returns host tensors ``reward, reward_raw, reset, terminated`` (valid on return); the observation buffers stay on
+        the device for the policy (``self.obs_buf`` / ``self.obs_norm``)."""
+        keys = [k for k in self._HOST_KEYS if k in host and (self.cfg.use_power_reward or not k.startswith("dof_"))]
+        if not hasattr(self, "_dev_in"):
+            self._dev_in = {k: torch.empty(host[k].shape, dtype=host[k].dtype, device=self.device) for k in keys}
+            self._host_out = {"reward": torch.empty(self.N, dtype=torch.float32).pin_memory(),
+                              "reward_raw": torch.empty((self.N, self.raw_dim), dtype=torch.float32).pin_memory(),
+                              "reset": torch.empty(self.N, dtype=torch.bool).pin_memory(),
+                              "terminated": torch.empty(self.N, dtype=torch.bool).pin_memory()}
+            self.host_h2d_bytes = sum(host[k].numel() * host[k].element_size() for k in keys)
+            self.host_d2h_bytes = sum(v.numel() * v.element_size() for v in self._host_out.values())
+        for k in keys:
+            if host[k].is_cuda:
+                raise RuntimeError("step_host expects host tensors; use __call__ for device-resident inputs")
+            self._dev_in[k].copy_(host[k], non_blocking=True)
+        d = self._dev_in
+        out = self(d["body_state"], d["progress"], d["start_time"], d["start_offset"], d["motion_ids"], d["global_offset"],
+                   d.get("dof_force"), d.get("dof_vel"))
+        for k, v in self._host_out.items():
+            v.copy_(out[k], non_blocking=True)
+        torch.cuda.current_stream(self.device).synchronize()
+        return self._host_out
