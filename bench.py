@@ -171,8 +171,8 @@ def workload_config(envs, world, sample_note=None):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=64)
-    ap.add_argument("--warmup", type=int, default=8)
+    ap.add_argument("--steps", type=int, default=2000)
+    ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--envs", type=int, default=65536, help="envs per GPU")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -310,10 +310,10 @@ def main():
         if world == 1 and not args.no_cpu_baseline:
             threads = os.cpu_count() or 1
             host_tables = {k: v.cpu() for k, v in T.items()}
-            sample = 8192
-            rate, spent = cpu_port_rate(sample, iters=5, warmup=2, threads=threads, tables_host=host_tables)
+            sample = N
+            rate, spent = cpu_port_rate(sample, iters=20, warmup=2, threads=threads, tables_host=host_tables)
             line["cpu_baseline"] = {"value": rate, "unit": "env-steps/s", "cores": threads, "kind": "port",
-                                    "sample": f"{sample} envs x 5 steps of the same workload ({spent:.1f} s), torch-CPU eager port of the "
+                                    "sample": f"{sample} envs x 20 steps of the same workload ({spent:.1f} s), torch-CPU eager port of the "
                                               "reference functions (oracle/torch_port.py) + C c_gae restatement"}
         print(json.dumps(line), flush=True)
     if world > 1:

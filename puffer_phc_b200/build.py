@@ -47,7 +47,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
     if not force and not needs_build():
         return LIB_PATH
     os.makedirs(LIB_DIR, exist_ok=True)
-    cmd = [_nvcc(), *NVCC_FLAGS, "-o", LIB_PATH, *sources()]
+    extra = os.environ.get("PHC_NVCC_EXTRA", "").split()      # e.g. -DST_MIN_CTAS=2 for tuning experiments
+    cmd = [_nvcc(), *NVCC_FLAGS, *extra, "-o", LIB_PATH, *sources()]
     if verbose:
         cmd += ["-Xptxas", "-v"]
         print(" ".join(cmd))

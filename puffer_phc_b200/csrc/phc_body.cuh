@@ -16,7 +16,7 @@ PHC_HD BodyState blend_frames(const BodyState& a, const BodyState& b, float blen
     const float om = 1.0f - blend;
     BodyState r;
     r.p = V3{lerp(a.p.x, b.p.x, om, blend) + off.x, lerp(a.p.y, b.p.y, om, blend) + off.y, lerp(a.p.z, b.p.z, om, blend) + off.z};
-    r.q = slerp(a.q, b.q, blend);
+    r.q = slerp_rcp(a.q, b.q, blend);
     r.v = V3{lerp(a.v.x, b.v.x, om, blend), lerp(a.v.y, b.v.y, om, blend), lerp(a.v.z, b.v.z, om, blend)};
     r.w = V3{lerp(a.w.x, b.w.x, om, blend), lerp(a.w.y, b.w.y, om, blend), lerp(a.w.z, b.w.z, om, blend)};
     return r;
@@ -53,6 +53,25 @@ PHC_HD void reward_terms_body(const BodyState& b, const BodyState& r, float& sp,
     sr = ang * ang;
     sv = mean_sq3(r.v - b.v);
     sa = mean_sq3(r.w - b.w);
+}
+
+// Fused-step flavour of the per-body reward terms: plain sums of squares (the two means become one
+// multiplication per env) and the closed-form squared angle; <= a few ulp from reward_terms_body.
+PHC_HD void reward_terms_body_fast(const BodyState& b, const BodyState& r, float& sp, float& sr, float& sv, float& sa) {
+    sp = sum_sq3(r.p - b.p);
+    sr = quat_angle_sq(quat_mul(r.q, quat_conj(b.q)));
+    sv = sum_sq3(r.v - b.v);
+    sa = sum_sq3(r.w - b.w);
+}
+
+// env-level tail for reward_terms_body_fast: sp/sv/sa are sums over J bodies x 3 components, sr over J bodies.
+PHC_HD float reward_from_sq_sums(float sp, float sr, float sv, float sa, float J, const float* k, const float* w, float* raw) {
+    const float inv3j = 1.0f / (3.0f * J), invj = 1.0f / J;
+    raw[0] = expf(-k[0] * (sp * inv3j));
+    raw[1] = expf(-k[1] * (sr * invj));
+    raw[2] = expf(-k[2] * (sv * inv3j));
+    raw[3] = expf(-k[3] * (sa * inv3j));
+    return ((w[0] * raw[0] + w[1] * raw[1]) + w[2] * raw[2]) + w[3] * raw[3];
 }
 
 // compute_imitation_reward, env-level tail (common.py:300-320): means over J, exp kernels, weighted sum.

@@ -128,6 +128,17 @@ PHC_HD float quat_angle(Q4 q) {
     return atan2f(sinf(a), cosf(a));
 }
 
+// Squared rotation angle of q for the rotation reward (common.py:304-306).  normalize_angle(2 acos w) is
+// 2 acos w wrapped into (-pi, pi]; only its square is used, so the wrap is done in closed form instead of the
+// reference's atan2(sin, cos) round trip (equal to a few ulp; the round trip itself carries ~5e-7 of noise).
+PHC_HD float quat_angle_sq(Q4 q) {
+    float s = sqrtf(1.0f - q.w * q.w);
+    if (!(fabsf(s) > 1e-5f)) return 0.0f;
+    float a = 2.0f * acosf(q.w);
+    if (a > 3.14159265358979323846f) a = a - 6.28318530717958647692f;
+    return a * a;
+}
+
 // quat_to_exp_map (torch_utils.py:144-150)
 PHC_HD V3 quat_exp_map(Q4 q) {
     float s = sqrtf(1.0f - q.w * q.w);
@@ -154,6 +165,23 @@ PHC_HD Q4 slerp(Q4 q0, Q4 q1, float t) {
     return Q4{ra * q0.x + rb * q1.x, ra * q0.y + rb * q1.y, ra * q0.z + rb * q1.z, ra * q0.w + rb * q1.w};
 }
 
+// Same slerp for the fused step: identical branch decisions (they depend on c and s only), but one IEEE
+// reciprocal shared by the two ratios instead of two divisions (<= 1 ulp from slerp()).
+PHC_HD Q4 slerp_rcp(Q4 q0, Q4 q1, float t) {
+    float c = ((q0.x * q1.x + q0.y * q1.y) + q0.z * q1.z) + q0.w * q1.w;
+    if (c < 0.0f) { q1.x = -q1.x; q1.y = -q1.y; q1.z = -q1.z; q1.w = -q1.w; }
+    c = fabsf(c);
+    if (c >= 1.0f) return q0;
+    float s = sqrtf(1.0f - c * c);
+    if (fabsf(s) < 0.001f)
+        return Q4{0.5f * q0.x + 0.5f * q1.x, 0.5f * q0.y + 0.5f * q1.y, 0.5f * q0.z + 0.5f * q1.z, 0.5f * q0.w + 0.5f * q1.w};
+    float h = acosf(c);
+    float inv = 1.0f / s;
+    float ra = sinf((1.0f - t) * h) * inv;
+    float rb = sinf(t * h) * inv;
+    return Q4{ra * q0.x + rb * q1.x, ra * q0.y + rb * q1.y, ra * q0.z + rb * q1.z, ra * q0.w + rb * q1.w};
+}
+
 // lerp as written in get_motion_state (motion_lib.py:596-603): (1-b)*x0 + b*x1
 PHC_HD float lerp(float a, float b, float one_m, float t) { return one_m * a + t * b; }
 
@@ -162,5 +190,7 @@ PHC_HD float norm3(V3 d) { return sqrtf(fmaf(d.z, d.z, fmaf(d.y, d.y, d.x * d.x)
 
 // mean over xyz of squares: ((x^2 + y^2) + z^2) / 3  ((diff**2).mean(dim=-1), common.py:300)
 PHC_HD float mean_sq3(V3 d) { return ((d.x * d.x + d.y * d.y) + d.z * d.z) / 3.0f; }
+// sum of squares only; the /3 and /J of the two means are applied once per env (reward_from_sq_sums)
+PHC_HD float sum_sq3(V3 d) { return (d.x * d.x + d.y * d.y) + d.z * d.z; }
 
 }  // namespace phc

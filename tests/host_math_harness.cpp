@@ -54,7 +54,7 @@ extern "C" int harness_step(const phc_motion_tables* T, const phc_step_in* in, c
             const float* sj = sim + REC * j;
             const BodyState body{V3{sj[0], sj[1], sj[2]}, Q4{sj[3], sj[4], sj[5], sj[6]}, V3{sj[7], sj[8], sj[9]}, V3{sj[10], sj[11], sj[12]}};
             const BodyState r0 = blend_frames(frame(T, a0 + ls, j), frame(T, a1 + ls, j), bla, off);
-            reward_terms_body(body, r0, sp[j], sr[j], sv[j], sa[j]);
+            reward_terms_body_fast(body, r0, sp[j], sr[j], sv[j], sa[j]);
             if ((cfg->reset_body_mask >> j) & 1u) {
                 dist[j] = norm3(body.p - r0.p);
                 over = over || (dist[j] > in->term_dist[j]);
@@ -76,7 +76,7 @@ extern "C" int harness_step(const phc_motion_tables* T, const phc_step_in* in, c
             fallen = fallen && (prog > 1);
         }
         float raw[4];
-        float rew = reward_from_sums(butterfly_sum(sp), butterfly_sum(sr), butterfly_sum(sv), butterfly_sum(sa), (float)NB, cfg->k, cfg->w, raw);
+        float rew = reward_from_sq_sums(butterfly_sum(sp), butterfly_sum(sr), butterfly_sum(sv), butterfly_sum(sa), (float)NB, cfg->k, cfg->w, raw);
         float* rr = out->reward_raw + e * out->raw_stride;
         memcpy(rr, raw, sizeof(raw));
         if (in->dof_force) {

@@ -61,7 +61,7 @@ def _run(harness, T, S, term, mask, use_mean, power):
 def test_kernel_math_vs_reference(harness, golden, tn, sn):
     T, S = golden[tn], golden[sn]
     obs, rew, raw, rs, tm = _run(harness, T, S, 0.25, 0xFFFFFF, False, True)
-    assert_close(obs, S["obs"], what="obs")
+    assert_close(obs, S["obs"], what="obs", row_scale=True)
     assert_close(rew, S["reward"], what="reward")
     assert_close(raw, S["reward_raw"], what="reward_raw")
     assert_equal(rs, S["reset_train"], "reset")

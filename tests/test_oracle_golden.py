@@ -61,9 +61,9 @@ def test_functions_on_reference_states(golden, tn, sn):
     assert_close(rew, S["reward_nopower"], what="reward")
     assert_close(raw, S["reward_raw4"], what="reward_raw")
     obs_self = co.self_obs(bp, br, bv, ba)
-    assert_close(obs_self, S["obs"][:, :358], what="self obs")
+    assert_close(obs_self, S["obs"][:, :358], what="self obs", row_scale=True)
     obs_task = co.imitation_obs_v6(bp[:, 0], br[:, 0], bp, br, bv, ba, *r1)
-    assert_close(obs_task, S["obs"][:, 358:], what="task obs")
+    assert_close(obs_task, S["obs"][:, 358:], what="task obs", row_scale=True)
     n = 32
     assert_close(co.self_obs(bp[:n], br[:n], bv[:n], ba[:n], local_root_obs=False, root_height_obs=False, upright=False),
                  S["self_obs_variant"], what="self obs variant flags")
@@ -88,7 +88,7 @@ def test_full_step(golden, tn, sn):
     args = (tab, S["in_body_state"], S["in_progress"], S["in_start_time"], S["in_start_offset"], S["in_motion_ids"],
             S["in_global_offset"], 1.0 / 30.0, K, W)
     r = co.step(*args, np.full(24, 0.25, np.float32), dof_force=S["in_dof_force"], dof_vel=S["in_dof_vel"], want_ref=True)
-    assert_close(r["obs"], S["obs"], what="obs")
+    assert_close(r["obs"], S["obs"], what="obs", row_scale=True)
     assert_close(r["reward"], S["reward"], what="reward")
     assert_close(r["reward_raw"], S["reward_raw"], what="reward_raw")
     assert_equal(r["reset"], S["reset_train"], "reset")
