@@ -117,6 +117,41 @@ PHC_HD void heading_quat(float heading, float& qz, float& qw) {
     qw = cs / n;
 }
 
+// Heading quaternion without the atan2 -> sin/cos round trip: with (dx, dy) the rotated x axis projected on the
+// ground plane, cos h = dx/r and sin h = dy/r, and the half-angle identities give (sin(h/2), cos(h/2)) directly
+// (the branch keeps the square root away from cancellation).  Equal to heading_quat(calc_heading(q)) to a few ulp;
+// used by the fused step, whose heading only feeds fp32 observation values (tolerance 1e-5), never a flag.
+PHC_HD void heading_quat_direct(Q4 q, float& qz, float& qw) {
+    float s = 2.0f * (q.w * q.w) - 1.0f;
+    float dx = s + (q.x * q.x) * 2.0f;
+    float dy = (q.z * q.w) * 2.0f + (q.y * q.x) * 2.0f;
+    float r = sqrtf(dx * dx + dy * dy);
+    if (!(r > 0.0f)) { qz = 0.0f; qw = 1.0f; return; }      // atan2(0, 0) = 0 in the reference
+    float inv = 1.0f / r;
+    float ch = dx * inv, sh = dy * inv;
+    if (ch >= 0.0f) {
+        qw = sqrtf(0.5f * (1.0f + ch));
+        qz = sh / (2.0f * qw);
+    } else {
+        float z = sqrtf(0.5f * (1.0f - ch));
+        qz = sh < 0.0f ? -z : z;
+        qw = sh / (2.0f * qz);
+    }
+}
+
+// sin(x) for x in [0, pi/2] (the only range slerp needs: x = t * acos(c), c in [0,1), t in [0,1]):
+// odd polynomial through x^13 in Horner form, relative error < 1e-7 (about 1 ulp), no range reduction.
+PHC_HD float sin_0_halfpi(float x) {
+    const float x2 = x * x;
+    float p = 1.6059043836821613e-10f;                  //  1/13!
+    p = fmaf(p, x2, -2.5052108385441720e-08f);          // -1/11!
+    p = fmaf(p, x2, 2.7557319223985893e-06f);           //  1/9!
+    p = fmaf(p, x2, -1.9841269841269841e-04f);          // -1/7!
+    p = fmaf(p, x2, 8.3333333333333332e-03f);           //  1/5!
+    p = fmaf(p, x2, -1.6666666666666666e-01f);          // -1/3!
+    return fmaf(x * x2, p, x);
+}
+
 // remove_base_rot (reference puffer_phc/envs/common.py:15-19), used when upright == false.
 PHC_HD Q4 remove_base_rot(Q4 q) { return quat_mul(q, Q4{-0.5f, -0.5f, -0.5f, 0.5f}); }
 
@@ -166,7 +201,8 @@ PHC_HD Q4 slerp(Q4 q0, Q4 q1, float t) {
 }
 
 // Same slerp for the fused step: identical branch decisions (they depend on c and s only), but one IEEE
-// reciprocal shared by the two ratios instead of two divisions (<= 1 ulp from slerp()).
+// reciprocal shared by the two ratios instead of two divisions, and a bounded-range polynomial sine
+// (the arguments lie in [0, pi/2]); a few ulp from slerp().
 PHC_HD Q4 slerp_rcp(Q4 q0, Q4 q1, float t) {
     float c = ((q0.x * q1.x + q0.y * q1.y) + q0.z * q1.z) + q0.w * q1.w;
     if (c < 0.0f) { q1.x = -q1.x; q1.y = -q1.y; q1.z = -q1.z; q1.w = -q1.w; }
@@ -177,8 +213,8 @@ PHC_HD Q4 slerp_rcp(Q4 q0, Q4 q1, float t) {
         return Q4{0.5f * q0.x + 0.5f * q1.x, 0.5f * q0.y + 0.5f * q1.y, 0.5f * q0.z + 0.5f * q1.z, 0.5f * q0.w + 0.5f * q1.w};
     float h = acosf(c);
     float inv = 1.0f / s;
-    float ra = sinf((1.0f - t) * h) * inv;
-    float rb = sinf(t * h) * inv;
+    float ra = sin_0_halfpi((1.0f - t) * h) * inv;
+    float rb = sin_0_halfpi(t * h) * inv;
     return Q4{ra * q0.x + rb * q1.x, ra * q0.y + rb * q1.y, ra * q0.z + rb * q1.z, ra * q0.w + rb * q1.w};
 }
 

@@ -5,31 +5,53 @@
 // compute_imitation_observations_v6, and optionally RunningNorm.forward plus the column moments that
 // RunningNorm.update needs (policies/running_norm.py:15-34).
 //
-// Mapping: persistent CTAs of 16 warps; each iteration a CTA owns 8 consecutive envs and TWO warps work on
-// each env, lane j = body j:
-//   role A (warps 0-7):  heading quaternion (handed to role B through shared memory + a named barrier),
-//                        reference state at t  -> reward terms, termination test, power term, self observation
-//   role B (warps 8-15): reference state at t+1 -> imitation (task) observation
-// Splitting the env halves the per-warp dependency chain and the live register state (2 frames per warp
-// instead of 4), which is what bounds this kernel (it is latency-, not bandwidth-limited at 1 warp/env).
-// The 8 PhysX records (8 x 1248 B) of the NEXT iteration are prefetched with cp.async while the current
-// tile is written out.  The 8 x 934-float observation tile is assembled in shared memory and leaves the SM
-// as one contiguous, 16-byte aligned 29.9 KB block (float4 stores); the normalised copy and the fp64 column
-// moments are produced from the same tile by column-owning threads (mean / 1/sqrt(var+eps) in registers).
+// Design (persistent, warp-specialised, one CTA per SM):
+//   * 2*S compute warps: each iteration the CTA owns S consecutive envs and TWO warps work on each env,
+//     lane j = body j:   role A: reference at t   -> reward terms, termination test, power term, self obs
+//                        role B: reference at t+1 -> imitation (task) observation
+//     Every compute warp owns a private 3 x 1248 B shared-memory buffer (PhysX record + its two bracketing
+//     reference frames).  The NEXT env's record and frames are fetched with cp.async right after the current
+//     ones have been read into registers, so the gathers fly during ~800 instructions of math and never
+//     occupy registers (the kernel is latency-bound, not bandwidth-bound, without this).
+//   * 4 writer warps: the S x 934-float observation tile is double-buffered in shared memory.  When a tile is
+//     full (mbarrier) the writers send it to HBM as ONE contiguous 16-byte aligned block with a TMA bulk
+//     store (cp.async.bulk), write the RunningNorm-normalised copy and accumulate the fp64 column moments
+//     from the same tile (column-owning threads keep mean, 1/sqrt(var+eps) and the accumulators in registers),
+//     then release the tile (mbarrier).  Compute warps never wait for stores.
+//   * 1 planner warp: lane = (env slot, role).  It reads the per-env scalars (coalesced across envs), does the
+//     id -> motion-meta lookups and the frame-index / blend arithmetic (bit-exact op order) one iteration ahead and
+//     leaves a 48-byte plan per compute warp in shared memory, so compute warps never execute (32x redundantly)
+//     or wait on that dependent load chain.
+//   * Body reductions are warp shuffles; the flag-critical chain keeps the reference's fp32 op order.
 #include "phc_body.cuh"
 
 namespace phc {
 
-#ifndef ST_ENVS_PER_CTA
-#define ST_ENVS_PER_CTA 8
+#ifndef ST_SLOTS
+#define ST_SLOTS 8                                   // envs per CTA iteration (multiple of 4: tiles stay 16-byte aligned)
 #endif
-constexpr int ST_ENVS = ST_ENVS_PER_CTA;         // envs per CTA iteration (4 or 8; tiles of 4+ rows stay 16-byte aligned)
-constexpr int ST_WARPS = 2 * ST_ENVS;            // two warps (roles A, B) per env
-constexpr int ST_THREADS = ST_WARPS * 32;        // 512
-#ifndef ST_MIN_CTAS
-#define ST_MIN_CTAS 2
+constexpr int ST_ENVS = ST_SLOTS;
+constexpr int ST_CWARPS = 2 * ST_ENVS;               // compute warps
+#ifndef ST_CHINT
+#define ST_CHINT 0
 #endif
-constexpr int ST_COLS_PER_THREAD = (OBS_W + ST_THREADS - 1) / ST_THREADS;   // 2
+#ifndef ST_WHINT
+#define ST_WHINT 400
+#endif
+#ifndef ST_WRITERS
+#define ST_WRITERS 4
+#endif
+constexpr int ST_WWARPS = ST_WRITERS;                // writer warps
+// register budget: the register file holds 20 warps x 96 registers or 21-24 warps x 80
+#ifndef ST_MAXREG
+#define ST_MAXREG (((2 * ST_SLOTS + ST_WRITERS + 1) <= 20) ? 96 : 80)
+#endif
+constexpr int ST_WTHREADS = ST_WWARPS * 32;
+constexpr int ST_THREADS = (ST_CWARPS + ST_WWARPS + 1) * 32;     // + the planner warp
+constexpr int ST_WPAIRS = (OBS_W / 2 + ST_WTHREADS - 1) / ST_WTHREADS;  // column pairs owned by a writer thread
+constexpr int ST_DOF_F = 144;                        // dof_force (69, padded to 72) | dof_vel (69, padded to 72)
+constexpr int ST_WBUF_F = 3 * FRAME_F + ST_DOF_F;    // per compute warp: sim record | frame 0 | frame 1 | dof force/vel
+constexpr unsigned SPIN_LIMIT = 1u << 28;            // a stuck mbarrier traps instead of hanging the GPU
 
 struct StepArgs {
     phc_motion_tables t;
@@ -37,27 +59,141 @@ struct StepArgs {
     phc_step_cfg cfg;
     phc_step_out out;
     int sim_vec;          // body_state rows are 16-byte aligned -> 16-byte cp.async staging
-    int obs_vec;          // obs tiles are contiguous and 16-byte aligned -> float4 tile stores
-    int64_t num_blocks;   // ceil(N / 8)
+    int obs_vec;          // obs tiles are contiguous and 16-byte aligned -> TMA bulk tile stores
+    int64_t num_blocks;   // ceil(N / S)
 };
 
-template <bool PACKED>
-__device__ __forceinline__ BodyState load_frame(const phc_motion_tables& T, int64_t f, int j) {
-    BodyState s;
-    if (PACKED) {
-        const float* base = T.packed + f * FRAME_F;
-        s.p = ldg3(base + 3 * j);
-        s.q = ldg4a(base + 72 + 4 * j);
-        s.v = ldg3(base + 168 + 3 * j);
-        s.w = ldg3(base + 240 + 3 * j);
-    } else {
-        const int64_t r = f * NB + j;
-        s.p = ldg3(T.gts + r * 3);
-        s.q = ldg4a(T.grs + r * 4);
-        s.v = ldg3(T.gvs + r * 3);
-        s.w = ldg3(T.gavs + r * 3);
+// ---- async-copy / barrier primitives ------------------------------------------------------------------------
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async4(void* smem_dst, const void* gsrc) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// Compute warps poll (they are the critical path and rarely wait); writer / planner warps pass a suspend-time hint
+// so that the hardware parks them instead of letting their polls steal issue slots from the math warps.
+template <int HINT_NS>
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity) {
+    unsigned done = 0, spins = 0;
+    while (!done) {
+        if (HINT_NS > 0)
+            asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                         : "=r"(done) : "r"(smem_u32(bar)), "r"(parity), "n"(HINT_NS) : "memory");
+        else
+            asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                         : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+        if (!done && ++spins > SPIN_LIMIT) __trap();
     }
-    return s;
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void bulk_store(void* gdst, const void* smem_src, unsigned bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(smem_u32(smem_src)), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void writers_sync() { asm volatile("bar.sync 1, %0;" ::"n"(ST_WTHREADS) : "memory"); }
+// torch.clamp propagates NaN: min.NaN / max.NaN do too (fminf / fmaxf would drop it)
+__device__ __forceinline__ float clamp_nan(float y, float lim) {
+    float r;
+    asm("max.NaN.f32 %0, %1, %2;" : "=f"(r) : "f"(y), "f"(-lim));
+    asm("min.NaN.f32 %0, %0, %1;" : "+f"(r) : "f"(lim));
+    return r;
+}
+
+// ---- what a compute warp needs to know about its env for one role (written by the planner warp) -----------------
+struct EnvPlan {
+    int64_t f0, f1;      // global frame rows (frame index + length_starts)
+    float blend, t, mlen;
+    float offx, offy, offz;
+    int prog;
+    int valid;
+};
+
+// Planner lane: per-env scalars, motion meta and the role's frame-blend (reference op order, bit-exact).
+__device__ __forceinline__ EnvPlan make_plan(const StepArgs& a, int64_t e, int role) {
+    const phc_motion_tables& T = a.t;
+    const phc_step_in& in = a.in;
+    EnvPlan p;
+    p.valid = e < in.N;
+    if (!p.valid) { p.f0 = p.f1 = 0; p.blend = p.t = p.mlen = p.offx = p.offy = p.offz = 0.0f; p.prog = 0; return p; }
+    const int64_t id = __ldg(in.motion_ids + e);
+    const int16_t prog = __ldg(in.progress + e);
+    const float st = __ldg(in.start_time + e), so = __ldg(in.start_offset + e);
+    const float mdt = __ldg(T.motion_dt + id);
+    const int64_t nf = __ldg(T.num_frames + id), ls = __ldg(T.length_starts + id);
+    p.mlen = __ldg(T.motion_len + id);
+    p.offx = __ldg(in.global_offset + e * 3);
+    p.offy = __ldg(in.global_offset + e * 3 + 1);
+    p.offz = __ldg(in.global_offset + e * 3 + 2);
+    p.prog = prog;
+    // humanoid_phc.py:1233-1235 (t) and :1060-1064 (t+1: progress_buf + 1 stays int16)
+    const int16_t step = role == 0 ? prog : (int16_t)(prog + 1);
+    p.t = ((float)step * a.cfg.dt + st) + so;
+    int64_t i0, i1;
+    frame_blend(p.t, p.mlen, nf, mdt, i0, i1, p.blend);
+    p.f0 = i0 + ls;
+    p.f1 = i1 + ls;
+    return p;
+}
+
+// Stage one reference frame (pos 72 | rot 96 | vel 72 | ang 72 floats) into shared memory: 78 x 16-byte chunks.
+template <bool PACKED>
+__device__ __forceinline__ void stage_frame(const phc_motion_tables& T, int64_t f, float* dst, int lane) {
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        const int i = lane + 32 * k;
+        if (i < FRAME_F / 4) {
+            const float* src;
+            if (PACKED) src = T.packed + f * FRAME_F + 4 * i;
+            else if (i < 18) src = T.gts + f * 72 + 4 * i;
+            else if (i < 42) src = T.grs + f * 96 + 4 * (i - 18);
+            else if (i < 60) src = T.gvs + f * 72 + 4 * (i - 42);
+            else src = T.gavs + f * 72 + 4 * (i - 60);
+            cp_async16(dst + 4 * i, src);
+        }
+    }
+}
+
+// Async fetch of everything a compute warp reads for env e: PhysX record, its two frames, (role A) dof force / vel.
+template <bool PACKED>
+__device__ __forceinline__ void issue_env(const StepArgs& a, const EnvPlan& p, int64_t e, int role, float* wbuf, int lane) {
+    const phc_step_in& in = a.in;
+    const float* rec = in.body_state + e * in.env_stride;
+    if (a.sim_vec) {
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            const int i = lane + 32 * k;
+            if (i < SIM_F / 4) cp_async16(wbuf + 4 * i, rec + 4 * i);
+        }
+    } else {
+        for (int i = lane; i < SIM_F; i += 32) cp_async4(wbuf + i, rec + i);
+    }
+    stage_frame<PACKED>(a.t, p.f0, wbuf + FRAME_F, lane);
+    if (p.f1 != p.f0) stage_frame<PACKED>(a.t, p.f1, wbuf + 2 * FRAME_F, lane);
+    if (role == 0 && in.dof_force) {
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            const int c = lane + 32 * k;
+            if (c < NDOF) {
+                cp_async4(wbuf + 3 * FRAME_F + c, in.dof_force + e * NDOF + c);
+                cp_async4(wbuf + 3 * FRAME_F + 72 + c, in.dof_vel + e * NDOF + c);
+            }
+        }
+    }
+}
+
+__device__ __forceinline__ BodyState read_frame(const float* f, int j) {
+    return BodyState{ld3(f + 3 * j), ld4(f + 72 + 4 * j), ld3(f + 168 + 3 * j), ld3(f + 240 + 3 * j)};
 }
 
 __device__ __forceinline__ void store_ref(float* dst, int j, const BodyState& r) {
@@ -67,239 +203,252 @@ __device__ __forceinline__ void store_ref(float* dst, int j, const BodyState& r)
     st3(dst + 240 + 3 * j, r.w);
 }
 
-__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
-}
-__device__ __forceinline__ void cp_async4(void* smem_dst, const void* gsrc) {
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
-}
-__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
-// named barriers 1..8: one per env slot, 64 threads (the slot's role-A and role-B warps)
-__device__ __forceinline__ void pair_arrive(int slot) { asm volatile("bar.arrive %0, 64;" ::"r"(slot + 1) : "memory"); }
-__device__ __forceinline__ void pair_sync(int slot) { asm volatile("bar.sync %0, 64;" ::"r"(slot + 1) : "memory"); }
-// torch.clamp propagates NaN: min.NaN / max.NaN do too (fminf / fmaxf would drop it)
-__device__ __forceinline__ float clamp_nan(float y, float lim) {
-    float r;
-    asm("max.NaN.f32 %0, %1, %2;" : "=f"(r) : "f"(y), "f"(-lim));
-    asm("min.NaN.f32 %0, %0, %1;" : "+f"(r) : "f"(lim));
-    return r;
-}
-
-// stage the PhysX records (24 x 13 floats each) of the 8 envs of block `blk` into shared memory (async)
-__device__ __forceinline__ void stage_sim(const StepArgs& a, int64_t blk, float* sim, int tid) {
-    const int64_t e0 = blk * ST_ENVS;
-    const int rows = (int)((a.in.N - e0 < ST_ENVS) ? (a.in.N - e0) : ST_ENVS);
-    if (a.sim_vec) {
-        for (int i = tid; i < rows * (SIM_F / 4); i += ST_THREADS) {
-            const int r = i / (SIM_F / 4), c = i - r * (SIM_F / 4);
-            cp_async16(sim + r * SIM_F + 4 * c, a.in.body_state + (e0 + r) * a.in.env_stride + 4 * c);
-        }
-    } else {
-        for (int i = tid; i < rows * SIM_F; i += ST_THREADS) {
-            const int r = i / SIM_F, c = i - r * SIM_F;
-            cp_async4(sim + r * SIM_F + c, a.in.body_state + (e0 + r) * a.in.env_stride + c);
-        }
-    }
-}
-
 template <bool PACKED>
-__global__ void __launch_bounds__(ST_THREADS, ST_MIN_CTAS) step_fused_kernel(const StepArgs a) {
+__global__ void __maxnreg__(ST_MAXREG) step_fused_kernel(const StepArgs a) {   // one persistent CTA per SM
     extern __shared__ float4 smem4[];
-    float* tile = reinterpret_cast<float*>(smem4);                 // [8][934]
-    float* sim = tile + ST_ENVS * OBS_W;                           // [8][312]
-    float* s_head = sim + ST_ENVS * SIM_F;                         // [8][2]  heading quaternion (z, w) per env slot
+    float* tiles = reinterpret_cast<float*>(smem4);                          // [2][S][934]
+    float* wbufs = tiles + 2 * ST_ENVS * OBS_W;                              // [2S][3][312]
+    EnvPlan* plans = reinterpret_cast<EnvPlan*>(wbufs + ST_CWARPS * ST_WBUF_F);     // [2][2S]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(plans + 2 * ST_CWARPS);
+    uint64_t* full = bars;          // [2] tile b written by all compute warps
+    uint64_t* empty = bars + 2;     // [2] tile b drained by the writers
+    uint64_t* pfull = bars + 4;     // [2] plan set d written by the planner
+    uint64_t* pempty = bars + 6;    // [2] plan set d consumed by all compute warps
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int role = warp / ST_ENVS, slot = warp % ST_ENVS;                   // each SM sub-partition gets two A and two B warps
-    const phc_motion_tables& T = a.t;
     const phc_step_in& in = a.in;
     const phc_step_cfg& cfg = a.cfg;
     const phc_step_out& out = a.out;
-    const bool do_norm = out.obs_norm != nullptr;
-    const bool do_mom = out.moment_partials != nullptr;
 
-    // column-owning state for the tile phase: thread tid owns observation columns tid and tid + 512
-    float c_mean[ST_COLS_PER_THREAD], c_inv[ST_COLS_PER_THREAD];
-    double msum[ST_COLS_PER_THREAD], msq[ST_COLS_PER_THREAD];
-#pragma unroll
-    for (int u = 0; u < ST_COLS_PER_THREAD; ++u) {
-        const int c = tid + u * ST_THREADS;
-        msum[u] = 0.0; msq[u] = 0.0; c_mean[u] = 0.0f; c_inv[u] = 1.0f;
-        if (do_norm && c < OBS_W) {
-            c_mean[u] = __ldg(in.rms_mean + c);
-            c_inv[u] = 1.0f / sqrtf(__ldg(in.rms_var + c) + cfg.rms_eps);   // running_norm.py:17, one IEEE reciprocal per column
-        }
+    if (tid == 0) {
+        mbar_init(&full[0], ST_CWARPS); mbar_init(&full[1], ST_CWARPS);
+        mbar_init(&empty[0], 1); mbar_init(&empty[1], 1);
+        mbar_init(&pfull[0], 1); mbar_init(&pfull[1], 1);
+        mbar_init(&pempty[0], ST_CWARPS); mbar_init(&pempty[1], ST_CWARPS);
     }
-
-    float* my_tile = tile + slot * OBS_W;
-    const float* my_sim = sim + slot * SIM_F;
-
-    if ((int64_t)blockIdx.x < a.num_blocks) stage_sim(a, blockIdx.x, sim, tid);
-    cp_async_wait_all();
     __syncthreads();
 
-    for (int64_t blk = blockIdx.x; blk < a.num_blocks; blk += gridDim.x) {
-        const int64_t e = blk * ST_ENVS + slot;
-        if (e < in.N) {
-            // ---- per-env scalars (all lanes read the same addresses) ---------------------------------
-            const int64_t id = __ldg(in.motion_ids + e);
-            const int16_t prog = __ldg(in.progress + e);
-            const float st = __ldg(in.start_time + e), so = __ldg(in.start_offset + e);
-            const float mlen = __ldg(T.motion_len + id), mdt = __ldg(T.motion_dt + id);
-            const int64_t nf = __ldg(T.num_frames + id), ls = __ldg(T.length_starts + id);
-            const V3 off = ldg3(in.global_offset + e * 3);
-            const V3 root_p = ld3(my_sim);
-            const int j = lane;
+    if (warp < ST_CWARPS) {
+        // ====================================== compute warps ======================================
+        const int role = warp / ST_ENVS, slot = warp % ST_ENVS;
+        float* wbuf = wbufs + warp * ST_WBUF_F;
+        const int j = lane;
+        EnvPlan cur{};
+        if ((int64_t)blockIdx.x < a.num_blocks) {
+            mbar_wait<ST_CHINT>(&pfull[0], 0);
+            cur = plans[warp];
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&pempty[0]);
+            if (cur.valid) issue_env<PACKED>(a, cur, (int64_t)blockIdx.x * ST_ENVS + slot, role, wbuf, lane);
+        }
+        cp_async_commit();
+        int it = 0;
+        for (int64_t blk = blockIdx.x; blk < a.num_blocks; blk += gridDim.x, ++it) {
+            const int64_t e = blk * ST_ENVS + slot;
+            const bool valid = e < in.N;
+            const int b = it & 1;
+            float* my_tile = tiles + (b * ST_ENVS + slot) * OBS_W;
 
-            if (role == 0) {
-                // ================= role A: reference at t -> reward, reset, power, self observation ===========
-                const Q4 root_q = ld4(my_sim + 3);
-                float hz, hw;
-                heading_quat(calc_heading(root_q), hz, hw);      // upright start: no base-rot removal
-                if (lane == 0) { s_head[2 * slot] = hz; s_head[2 * slot + 1] = hw; }
-                __threadfence_block();
-                pair_arrive(slot);                               // role B picks the heading up with pair_sync
-
-                const float t0 = ((float)prog * cfg.dt + st) + so;                        // humanoid_phc.py:1233-1235
-                int64_t a0, a1;
-                float bla;
-                frame_blend(t0, mlen, nf, mdt, a0, a1, bla);
-                float sp = 0.0f, sr = 0.0f, sv = 0.0f, sa = 0.0f, dist = 0.0f;
-                bool over = false;
-                const bool in_mask = lane < NB && ((cfg.reset_body_mask >> lane) & 1u);
+            // ---- operands of this env: shared memory -> registers, blend the two frames ----------------
+            cp_async_wait_all();
+            __syncwarp();
+            BodyState body{}, ref{};
+            V3 root_p{};
+            Q4 root_q{0.0f, 0.0f, 0.0f, 1.0f};
+            float power = 0.0f;
+            if (valid) {
+                root_p = ld3(wbuf);
+                root_q = ld4(wbuf + 3);
                 if (lane < NB) {
-                    const BodyState A0 = load_frame<PACKED>(T, a0 + ls, j);
-                    const BodyState A1 = (a1 == a0) ? A0 : load_frame<PACKED>(T, a1 + ls, j);
-                    const float* sj = my_sim + REC * j;
-                    const BodyState body{ld3(sj), ld4(sj + 3), ld3(sj + 7), ld3(sj + 10)};
-                    float* o = my_tile;
-                    if (j == 0) o[0] = root_p.z;                                          // common.py:40
-                    self_obs_body(body, root_p, hz, hw, j, o + 1 + 3 * (j - 1), o + 70 + 6 * j, o + 214 + 3 * j, o + 286 + 3 * j);
-                    const BodyState r0 = blend_frames(A0, A1, bla, off);
-                    reward_terms_body_fast(body, r0, sp, sr, sv, sa);
-                    if (in_mask) {
-                        dist = norm3(body.p - r0.p);
-                        over = dist > __ldg(in.term_dist + j);
-                    }
-                    if (out.ref_state_t) store_ref(out.ref_state_t + e * FRAME_F, j, r0);
+                    const float* sj = wbuf + REC * j;
+                    body = BodyState{ld3(sj), ld4(sj + 3), ld3(sj + 7), ld3(sj + 10)};
+                    const BodyState F0 = read_frame(wbuf + FRAME_F, j);
+                    const BodyState F1 = (cur.f1 == cur.f0) ? F0 : read_frame(wbuf + 2 * FRAME_F, j);
+                    ref = blend_frames(F0, F1, cur.blend, V3{cur.offx, cur.offy, cur.offz});
                 }
-                sp = warp_sum(sp); sr = warp_sum(sr); sv = warp_sum(sv); sa = warp_sum(sa);
-                bool fallen = false;
-                if (cfg.enable_early_termination) {
-                    if (cfg.use_mean) {
-                        const float total = warp_sum(in_mask ? dist : 0.0f);
-                        const int first = __ffs(cfg.reset_body_mask) - 1;
-                        fallen = (total / (float)__popc(cfg.reset_body_mask & 0xffffffu)) > __ldg(in.term_dist + first);
-                    } else {
-                        fallen = __any_sync(FULL, over);
-                    }
-                    fallen = fallen && (prog > 1);                                        // common.py:354
-                }
-                float power = 0.0f;
-                if (in.dof_force) {                                                       // humanoid_phc.py:1295-1303
+                if (role == 0 && in.dof_force) {                                  // humanoid_phc.py:1295-1303
+                    const float* df = wbuf + 3 * FRAME_F;
 #pragma unroll
                     for (int k = 0; k < 3; ++k) {
                         const int c = lane + 32 * k;
-                        if (c < NDOF) power = power + fabsf(__ldg(in.dof_force + e * NDOF + c) * __ldg(in.dof_vel + e * NDOF + c));
+                        if (c < NDOF) power = power + fabsf(df[c] * df[72 + c]);
                     }
-                    power = warp_sum(power);
                 }
-                if (lane == 0) {
-                    float raw[4];
-                    float rew = reward_from_sq_sums(sp, sr, sv, sa, (float)NB, cfg.k, cfg.w, raw);
-                    float* rr = out.reward_raw + e * out.raw_stride;
-                    rr[0] = raw[0]; rr[1] = raw[1]; rr[2] = raw[2]; rr[3] = raw[3];
-                    if (in.dof_force) {
-                        float pr = -cfg.power_coef * power;
-                        if (prog <= 3) pr = 0.0f;
-                        rew = rew + pr;
-                        rr[4] = pr;
+            }
+            __syncwarp();
+            // ---- the buffer is free again: fetch the next env's record and frames behind the math ----------
+            EnvPlan nxt{};
+            {
+                const int64_t nblk = blk + gridDim.x;
+                if (nblk < a.num_blocks) {
+                    const int d = (it + 1) & 1;
+                    mbar_wait<ST_CHINT>(&pfull[d], ((it + 1) >> 1) & 1);
+                    nxt = plans[d * ST_CWARPS + warp];
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&pempty[d]);
+                    if (nxt.valid) issue_env<PACKED>(a, nxt, nblk * ST_ENVS + slot, role, wbuf, lane);
+                }
+                cp_async_commit();
+            }
+            if (it >= 2) mbar_wait<ST_CHINT>(&empty[b], ((it >> 1) - 1) & 1);           // tile buffer b released by the writers
+
+            if (valid) {
+                float hz, hw;
+                heading_quat_direct(root_q, hz, hw);                           // upright start: no base-rot removal
+                if (role == 0) {
+                    // ============ role A: reward, reset, power, self observation (reference at t) ============
+                    float sp = 0.0f, sr = 0.0f, sv = 0.0f, sa = 0.0f, dist = 0.0f;
+                    bool over = false;
+                    const bool in_mask = lane < NB && ((cfg.reset_body_mask >> lane) & 1u);
+                    if (lane < NB) {
+                        reward_terms_body_fast(body, ref, sp, sr, sv, sa);
+                        if (in_mask) {
+                            dist = norm3(body.p - ref.p);
+                            over = dist > __ldg(in.term_dist + j);
+                        }
+                        if (out.ref_state_t) store_ref(out.ref_state_t + e * FRAME_F, j, ref);
+                        float* o = my_tile;
+                        if (j == 0) o[0] = root_p.z;                                      // common.py:40
+                        self_obs_body(body, root_p, hz, hw, j, o + 1 + 3 * (j - 1), o + 70 + 6 * j, o + 214 + 3 * j, o + 286 + 3 * j);
                     }
-                    out.reward[e] = rew;
-                    out.terminated[e] = fallen ? 1 : 0;
-                    out.reset[e] = (t0 >= mlen) ? 1 : (fallen ? 1 : 0);                   // humanoid_phc.py:1315, common.py:362
-                }
-            } else {
-                // ================= role B: reference at t+1 -> imitation observation ==========================
-                const float t1 = ((float)(int16_t)(prog + 1) * cfg.dt + st) + so;         // humanoid_phc.py:1060-1064 (int16 + 1)
-                int64_t b0, b1;
-                float blb;
-                frame_blend(t1, mlen, nf, mdt, b0, b1, blb);
-                BodyState body, r1;
-                if (lane < NB) {
-                    const BodyState B0 = load_frame<PACKED>(T, b0 + ls, j);
-                    const BodyState B1 = (b1 == b0) ? B0 : load_frame<PACKED>(T, b1 + ls, j);
-                    const float* sj = my_sim + REC * j;
-                    body = BodyState{ld3(sj), ld4(sj + 3), ld3(sj + 7), ld3(sj + 10)};
-                    r1 = blend_frames(B0, B1, blb, off);
-                    if (out.ref_state_t1) store_ref(out.ref_state_t1 + e * FRAME_F, j, r1);
-                }
-                pair_sync(slot);
-                const float hz = s_head[2 * slot], hw = s_head[2 * slot + 1];
-                if (lane < NB) {
+                    sp = warp_sum(sp); sr = warp_sum(sr); sv = warp_sum(sv); sa = warp_sum(sa);
+                    bool fallen = false;
+                    if (cfg.enable_early_termination) {
+                        if (cfg.use_mean) {
+                            const float total = warp_sum(in_mask ? dist : 0.0f);
+                            const int first = __ffs(cfg.reset_body_mask) - 1;
+                            fallen = (total / (float)__popc(cfg.reset_body_mask & 0xffffffu)) > __ldg(in.term_dist + first);
+                        } else {
+                            fallen = __any_sync(FULL, over);
+                        }
+                        fallen = fallen && (cur.prog > 1);                                // common.py:354
+                    }
+                    if (in.dof_force) power = warp_sum(power);
+                    if (lane == 0) {
+                        float raw[4];
+                        float rew = reward_from_sq_sums(sp, sr, sv, sa, (float)NB, cfg.k, cfg.w, raw);
+                        float* rr = out.reward_raw + e * out.raw_stride;
+                        rr[0] = raw[0]; rr[1] = raw[1]; rr[2] = raw[2]; rr[3] = raw[3];
+                        if (in.dof_force) {
+                            float pr = -cfg.power_coef * power;
+                            if (cur.prog <= 3) pr = 0.0f;
+                            rew = rew + pr;
+                            rr[4] = pr;
+                        }
+                        out.reward[e] = rew;
+                        out.terminated[e] = fallen ? 1 : 0;
+                        out.reset[e] = (cur.t >= cur.mlen) ? 1 : (fallen ? 1 : 0);        // humanoid_phc.py:1315, common.py:362
+                    }
+                } else if (lane < NB) {
+                    // ============ role B: imitation observation (reference at t+1) ============================
+                    if (out.ref_state_t1) store_ref(out.ref_state_t1 + e * FRAME_F, j, ref);
                     float* q = my_tile + OBS_SELF;
-                    task_obs_body(body, r1, root_p, hz, hw, q + 3 * j, q + 72 + 6 * j, q + 216 + 3 * j, q + 288 + 3 * j,
+                    task_obs_body(body, ref, root_p, hz, hw, q + 3 * j, q + 72 + 6 * j, q + 216 + 3 * j, q + 288 + 3 * j,
                                   q + 360 + 3 * j, q + 432 + 6 * j);
                 }
             }
+            fence_proxy_async();            // tile rows were written by ordinary stores; the writers read them through TMA
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&full[b]);
+            cur = nxt;
         }
-        __syncthreads();     // the tile is complete and the sim records of this iteration are no longer needed
-
-        // ---- prefetch the next iteration's PhysX records while the tile is written out ----------------
-        const int64_t nxt = blk + gridDim.x;
-        if (nxt < a.num_blocks) stage_sim(a, nxt, sim, tid);
-
-        // ---- the CTA's 8 x 934 tile leaves as one contiguous block ------------------------------------
-        const int64_t e0 = blk * ST_ENVS;
-        const int rows = (int)((in.N - e0 < ST_ENVS) ? (in.N - e0) : ST_ENVS);
-        if (a.obs_vec) {
-            const int total = rows * OBS_W;
-            float4* dst = reinterpret_cast<float4*>(out.obs + e0 * OBS_W);
-            const float4* src = reinterpret_cast<const float4*>(tile);
-            const int n4 = total >> 2;
-            for (int i = tid; i < n4; i += ST_THREADS) dst[i] = src[i];
-            for (int i = (n4 << 2) + tid; i < total; i += ST_THREADS) out.obs[e0 * OBS_W + i] = tile[i];
-        }
-        if (!a.obs_vec || do_norm || do_mom) {
+        cp_async_wait_all();
+    } else if (warp < ST_CWARPS + ST_WWARPS) {
+        // ====================================== writer warps =======================================
+        const int wtid = tid - ST_CWARPS * 32;
+        const bool do_norm = out.obs_norm != nullptr;
+        const bool do_mom = out.moment_partials != nullptr;
+        // each writer thread owns ST_WPAIRS pairs of adjacent observation columns (float2 granularity: rows are 8-byte aligned)
+        float2 c_mean[ST_WPAIRS], c_inv[ST_WPAIRS];
+        double msum[ST_WPAIRS][2], msq[ST_WPAIRS][2];
 #pragma unroll
-            for (int u = 0; u < ST_COLS_PER_THREAD; ++u) {
-                const int c = tid + u * ST_THREADS;
+        for (int u = 0; u < ST_WPAIRS; ++u) {
+            const int c = 2 * (wtid + u * ST_WTHREADS);
+            msum[u][0] = msum[u][1] = msq[u][0] = msq[u][1] = 0.0;
+            c_mean[u] = make_float2(0.0f, 0.0f);
+            c_inv[u] = make_float2(1.0f, 1.0f);
+            if (do_norm && c < OBS_W) {      // running_norm.py:17, one IEEE reciprocal per column
+                c_mean[u] = make_float2(__ldg(in.rms_mean + c), __ldg(in.rms_mean + c + 1));
+                c_inv[u] = make_float2(1.0f / sqrtf(__ldg(in.rms_var + c) + cfg.rms_eps), 1.0f / sqrtf(__ldg(in.rms_var + c + 1) + cfg.rms_eps));
+            }
+        }
+        auto column_pass = [&](const float* tile, int64_t e0, int r) {
+#pragma unroll
+            for (int u = 0; u < ST_WPAIRS; ++u) {
+                const int c = 2 * (wtid + u * ST_WTHREADS);
                 if (c < OBS_W) {
-                    for (int r = 0; r < rows; ++r) {
-                        const float x = tile[r * OBS_W + c];
-                        if (!a.obs_vec) out.obs[(e0 + r) * out.obs_stride + c] = x;
-                        if (do_norm)   // (x - mean) / sqrt(var + eps) as a multiplication by the column's reciprocal (<= 1.5 ulp)
-                            out.obs_norm[(e0 + r) * out.obs_stride + c] = clamp_nan((x - c_mean[u]) * c_inv[u], cfg.rms_clip);
-                        if (do_mom) {
-                            const double xd = (double)x;
-                            msum[u] += xd;
-                            msq[u] = fma(xd, xd, msq[u]);          // xd*xd is exact in fp64, so this equals msq + xd*xd
-                        }
+                    const float2 x = *reinterpret_cast<const float2*>(tile + r * OBS_W + c);
+                    if (!a.obs_vec) { float* o = out.obs + (e0 + r) * out.obs_stride + c; o[0] = x.x; o[1] = x.y; }
+                    if (do_norm) {   // (x - mean) / sqrt(var + eps) as a multiplication by the column's reciprocal (<= 1.5 ulp)
+                        const float y0 = clamp_nan((x.x - c_mean[u].x) * c_inv[u].x, cfg.rms_clip);
+                        const float y1 = clamp_nan((x.y - c_mean[u].y) * c_inv[u].y, cfg.rms_clip);
+                        float* o = out.obs_norm + (e0 + r) * out.obs_stride + c;
+                        if (a.obs_vec) *reinterpret_cast<float2*>(o) = make_float2(y0, y1);
+                        else { o[0] = y0; o[1] = y1; }
+                    }
+                    if (do_mom) {    // xd*xd is exact in fp64, so fma(xd, xd, q) equals q + xd*xd
+                        const double x0 = (double)x.x, x1 = (double)x.y;
+                        msum[u][0] += x0; msq[u][0] = fma(x0, x0, msq[u][0]);
+                        msum[u][1] += x1; msq[u][1] = fma(x1, x1, msq[u][1]);
                     }
                 }
             }
+        };
+        int it = 0;
+        for (int64_t blk = blockIdx.x; blk < a.num_blocks; blk += gridDim.x, ++it) {
+            const int b = it & 1;
+            const float* tile = tiles + b * ST_ENVS * OBS_W;
+            const int64_t e0 = blk * ST_ENVS;
+            const int rows = (int)((in.N - e0 < ST_ENVS) ? (in.N - e0) : ST_ENVS);
+            mbar_wait<ST_WHINT>(&full[b], (it >> 1) & 1);
+            // ---- raw observations: one TMA bulk store of the whole tile (manual copy for odd tails / pitched rows) ----
+            const bool bulk = a.obs_vec && ((rows & 1) == 0);     // rows * 3736 B is a multiple of 16 for even rows
+            if (bulk) {
+                if (wtid == 0) bulk_store(out.obs + e0 * OBS_W, tile, (unsigned)(rows * OBS_W * sizeof(float)));
+            } else if (a.obs_vec) {
+                for (int i = wtid; i < rows * OBS_W; i += ST_WTHREADS) out.obs[e0 * OBS_W + i] = tile[i];
+            }
+            // ---- normalised copy + fp64 column moments from the same tile ----------------------------------------
+            if (!a.obs_vec || do_norm || do_mom) {
+                // rolled on purpose: three warp roles share the instruction cache, and the pairs give the ILP
+#pragma unroll 1
+                for (int r = 0; r < rows; ++r) column_pass(tile, e0, r);
+            }
+            if (bulk && wtid == 0) bulk_wait_read();     // the TMA engine has finished reading the tile from shared memory
+            writers_sync();
+            if (wtid == 0) mbar_arrive(&empty[b]);
         }
-        cp_async_wait_all();
-        __syncthreads();
-    }
-
-    if (do_mom) {
-        double* p = out.moment_partials + (int64_t)blockIdx.x * 2 * OBS_W;
+        if (wtid == 0) bulk_wait_all();
+        if (do_mom) {
+            double* p = out.moment_partials + (int64_t)blockIdx.x * 2 * OBS_W;
 #pragma unroll
-        for (int u = 0; u < ST_COLS_PER_THREAD; ++u) {
-            const int c = tid + u * ST_THREADS;
-            if (c < OBS_W) { p[c] = msum[u]; p[OBS_W + c] = msq[u]; }
+            for (int u = 0; u < ST_WPAIRS; ++u) {
+                const int c = 2 * (wtid + u * ST_WTHREADS);
+                if (c < OBS_W) { p[c] = msum[u][0]; p[c + 1] = msum[u][1]; p[OBS_W + c] = msq[u][0]; p[OBS_W + c + 1] = msq[u][1]; }
+            }
+        }
+    } else {
+        // ====================================== planner warp =======================================
+        int it = 0;
+        for (int64_t blk = blockIdx.x; blk < a.num_blocks; blk += gridDim.x, ++it) {
+            const int d = it & 1;
+            if (it >= 2) mbar_wait<ST_WHINT>(&pempty[d], ((it >> 1) - 1) & 1);
+            if (lane < ST_CWARPS) plans[d * ST_CWARPS + lane] = make_plan(a, blk * ST_ENVS + lane % ST_ENVS, lane / ST_ENVS);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&pfull[d]);
         }
     }
 }
 
-constexpr size_t ST_SMEM = (size_t)(ST_ENVS * OBS_W + ST_ENVS * SIM_F + 2 * ST_ENVS) * sizeof(float);
+constexpr size_t ST_SMEM = (size_t)(2 * ST_ENVS * OBS_W + ST_CWARPS * ST_WBUF_F) * sizeof(float) + 2 * ST_CWARPS * sizeof(EnvPlan) +
+                           8 * sizeof(uint64_t);
+static_assert(sizeof(EnvPlan) == 48 && ST_CWARPS <= 32, "plan record layout");
 
 }  // namespace phc
 
 using namespace phc;
 
-extern "C" int phc_step_num_partials(void) { return ST_MIN_CTAS * sm_count(); }
+extern "C" int phc_step_num_partials(void) { return sm_count(); }
 
 extern "C" int phc_step_fused(const phc_motion_tables* t, const phc_step_in* in, const phc_step_cfg* cfg,
                               const phc_step_out* out, phc_stream_t stream) {
@@ -322,15 +471,27 @@ extern "C" int phc_step_fused(const phc_motion_tables* t, const phc_step_in* in,
         PHC_REQUIRE(aligned16(t->packed), PHC_EALIGN, "%s: packed table must be 16-byte aligned", fn);
     } else {
         PHC_REQUIRE(t->gts && t->grs && t->gvs && t->gavs, PHC_EINVAL, "%s: gts/grs/gvs/gavs tables missing", fn);
-        PHC_REQUIRE(aligned16(t->grs), PHC_EALIGN, "%s: grs table must be 16-byte aligned", fn);
+        PHC_REQUIRE(aligned16(t->gts) && aligned16(t->grs) && aligned16(t->gvs) && aligned16(t->gavs), PHC_EALIGN,
+                    "%s: gts/grs/gvs/gavs tables must be 16-byte aligned", fn);
     }
-    // the grid is fixed (ST_MIN_CTAS CTAs per SM) so that the number of moment partial slots does not depend on N
+    // the grid is fixed (one persistent CTA per SM) so that the number of moment partial slots does not depend on N
     const int grid = phc_step_num_partials();
     StepArgs a{*t, *in, *cfg, *out, 0, 0, (in->N + ST_ENVS - 1) / ST_ENVS};
     a.sim_vec = aligned16(in->body_state) && (in->env_stride % 4 == 0);
-    a.obs_vec = out->obs_stride == OBS_W && aligned16(out->obs);
+    a.obs_vec = out->obs_stride == OBS_W && aligned16(out->obs) && (!out->obs_norm || aligned8(out->obs_norm));
     if (in->N == 0 && !out->moment_partials) return PHC_OK;
     cudaStream_t s = (cudaStream_t)stream;
+    static thread_local int smem_dev = -1;      // opt in to > 48 KB of dynamic shared memory once per device
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (smem_dev != dev) {
+        cudaError_t e1 = cudaFuncSetAttribute(step_fused_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ST_SMEM);
+        cudaError_t e2 = cudaFuncSetAttribute(step_fused_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ST_SMEM);
+        if (e1 != cudaSuccess || e2 != cudaSuccess)
+            return fail((int)(e1 != cudaSuccess ? e1 : e2), "%s: cudaFuncSetAttribute(%zu B smem): %s", fn, ST_SMEM,
+                        cudaGetErrorString(e1 != cudaSuccess ? e1 : e2));
+        smem_dev = dev;
+    }
     if (packed) step_fused_kernel<true><<<grid, ST_THREADS, ST_SMEM, s>>>(a);
     else step_fused_kernel<false><<<grid, ST_THREADS, ST_SMEM, s>>>(a);
     return check_launch(fn);

@@ -46,7 +46,7 @@ extern "C" int harness_step(const phc_motion_tables* T, const phc_step_in* in, c
         const Q4 root_q{sim[3], sim[4], sim[5], sim[6]};
         const V3 root_p{sim[0], sim[1], sim[2]};
         float hz, hw;
-        heading_quat(calc_heading(root_q), hz, hw);
+        heading_quat_direct(root_q, hz, hw);
         float sp[32] = {0}, sr[32] = {0}, sv[32] = {0}, sa[32] = {0}, dist[32] = {0};
         bool over = false;
         float* tile = out->obs + e * out->obs_stride;
