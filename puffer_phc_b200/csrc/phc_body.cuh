@@ -46,6 +46,17 @@ PHC_HD void self_obs_body(const BodyState& b, V3 root_pos, float hz, float hw, i
     put3(o_ang, rotate_z(-hz, hw, b.w));                                      // :85-89
 }
 
+// The same self observation split in two so that the fused step can balance its two warp roles.
+PHC_HD void self_obs_pos_rot(const BodyState& b, V3 root_pos, float hz, float hw, int j, float* o_pos, float* o_rot) {
+    const Q4 hinv{0.0f, 0.0f, -hz, hw};
+    if (j >= 1) put3(o_pos, rotate_z(-hz, hw, b.p - root_pos));               // :57-66
+    tan_norm(quat_mul(hinv, b.q), o_rot);                                     // :68-75
+}
+PHC_HD void self_obs_vel_ang(const BodyState& b, float hz, float hw, float* o_vel, float* o_ang) {
+    put3(o_vel, rotate_z(-hz, hw, b.v));                                      // :81-83
+    put3(o_ang, rotate_z(-hz, hw, b.w));                                      // :85-89
+}
+
 // compute_imitation_reward, per-body terms (common.py:298-316).
 PHC_HD void reward_terms_body(const BodyState& b, const BodyState& r, float& sp, float& sr, float& sv, float& sa) {
     sp = mean_sq3(r.p - b.p);

@@ -38,6 +38,9 @@ constexpr int ST_CWARPS = 2 * ST_ENVS;               // compute warps
 #ifndef ST_WHINT
 #define ST_WHINT 400
 #endif
+#ifndef ST_TILES
+#define ST_TILES 2                                   // observation tiles in flight between compute and writer warps
+#endif
 #ifndef ST_WRITERS
 #define ST_WRITERS 4
 #endif
@@ -206,14 +209,14 @@ __device__ __forceinline__ void store_ref(float* dst, int j, const BodyState& r)
 template <bool PACKED>
 __global__ void __maxnreg__(ST_MAXREG) step_fused_kernel(const StepArgs a) {   // one persistent CTA per SM
     extern __shared__ float4 smem4[];
-    float* tiles = reinterpret_cast<float*>(smem4);                          // [2][S][934]
-    float* wbufs = tiles + 2 * ST_ENVS * OBS_W;                              // [2S][3][312]
+    float* tiles = reinterpret_cast<float*>(smem4);                          // [ST_TILES][S][934]
+    float* wbufs = tiles + ST_TILES * ST_ENVS * OBS_W;                       // [2S][3 frames + dof]
     EnvPlan* plans = reinterpret_cast<EnvPlan*>(wbufs + ST_CWARPS * ST_WBUF_F);     // [2][2S]
     uint64_t* bars = reinterpret_cast<uint64_t*>(plans + 2 * ST_CWARPS);
-    uint64_t* full = bars;          // [2] tile b written by all compute warps
-    uint64_t* empty = bars + 2;     // [2] tile b drained by the writers
-    uint64_t* pfull = bars + 4;     // [2] plan set d written by the planner
-    uint64_t* pempty = bars + 6;    // [2] plan set d consumed by all compute warps
+    uint64_t* full = bars;                    // [ST_TILES] tile b written by all compute warps
+    uint64_t* empty = bars + ST_TILES;        // [ST_TILES] tile b drained by the writers
+    uint64_t* pfull = bars + 2 * ST_TILES;    // [2] plan set d written by the planner
+    uint64_t* pempty = pfull + 2;             // [2] plan set d consumed by all compute warps
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const phc_step_in& in = a.in;
@@ -221,8 +224,7 @@ __global__ void __maxnreg__(ST_MAXREG) step_fused_kernel(const StepArgs a) {   /
     const phc_step_out& out = a.out;
 
     if (tid == 0) {
-        mbar_init(&full[0], ST_CWARPS); mbar_init(&full[1], ST_CWARPS);
-        mbar_init(&empty[0], 1); mbar_init(&empty[1], 1);
+        for (int i = 0; i < ST_TILES; ++i) { mbar_init(&full[i], ST_CWARPS); mbar_init(&empty[i], 1); }
         mbar_init(&pfull[0], 1); mbar_init(&pfull[1], 1);
         mbar_init(&pempty[0], ST_CWARPS); mbar_init(&pempty[1], ST_CWARPS);
     }
@@ -246,7 +248,7 @@ __global__ void __maxnreg__(ST_MAXREG) step_fused_kernel(const StepArgs a) {   /
         for (int64_t blk = blockIdx.x; blk < a.num_blocks; blk += gridDim.x, ++it) {
             const int64_t e = blk * ST_ENVS + slot;
             const bool valid = e < in.N;
-            const int b = it & 1;
+            const int b = it % ST_TILES, use = it / ST_TILES;                  // use-th time tile buffer b is filled
             float* my_tile = tiles + (b * ST_ENVS + slot) * OBS_W;
 
             // ---- operands of this env: shared memory -> registers, blend the two frames ----------------
@@ -290,7 +292,7 @@ __global__ void __maxnreg__(ST_MAXREG) step_fused_kernel(const StepArgs a) {   /
                 }
                 cp_async_commit();
             }
-            if (it >= 2) mbar_wait<ST_CHINT>(&empty[b], ((it >> 1) - 1) & 1);           // tile buffer b released by the writers
+            if (use >= 1) mbar_wait<ST_CHINT>(&empty[b], (use - 1) & 1);               // tile buffer b released by the writers
 
             if (valid) {
                 float hz, hw;
@@ -309,7 +311,7 @@ __global__ void __maxnreg__(ST_MAXREG) step_fused_kernel(const StepArgs a) {   /
                         if (out.ref_state_t) store_ref(out.ref_state_t + e * FRAME_F, j, ref);
                         float* o = my_tile;
                         if (j == 0) o[0] = root_p.z;                                      // common.py:40
-                        self_obs_body(body, root_p, hz, hw, j, o + 1 + 3 * (j - 1), o + 70 + 6 * j, o + 214 + 3 * j, o + 286 + 3 * j);
+                        self_obs_pos_rot(body, root_p, hz, hw, j, o + 1 + 3 * (j - 1), o + 70 + 6 * j);   // vel / ang blocks: role B
                     }
                     sp = warp_sum(sp); sr = warp_sum(sr); sv = warp_sum(sv); sa = warp_sum(sa);
                     bool fallen = false;
@@ -342,6 +344,7 @@ __global__ void __maxnreg__(ST_MAXREG) step_fused_kernel(const StepArgs a) {   /
                 } else if (lane < NB) {
                     // ============ role B: imitation observation (reference at t+1) ============================
                     if (out.ref_state_t1) store_ref(out.ref_state_t1 + e * FRAME_F, j, ref);
+                    self_obs_vel_ang(body, hz, hw, my_tile + 214 + 3 * j, my_tile + 286 + 3 * j);      // balances the two roles
                     float* q = my_tile + OBS_SELF;
                     task_obs_body(body, ref, root_p, hz, hw, q + 3 * j, q + 72 + 6 * j, q + 216 + 3 * j, q + 288 + 3 * j,
                                   q + 360 + 3 * j, q + 432 + 6 * j);
@@ -396,11 +399,11 @@ __global__ void __maxnreg__(ST_MAXREG) step_fused_kernel(const StepArgs a) {   /
         };
         int it = 0;
         for (int64_t blk = blockIdx.x; blk < a.num_blocks; blk += gridDim.x, ++it) {
-            const int b = it & 1;
+            const int b = it % ST_TILES;
             const float* tile = tiles + b * ST_ENVS * OBS_W;
             const int64_t e0 = blk * ST_ENVS;
             const int rows = (int)((in.N - e0 < ST_ENVS) ? (in.N - e0) : ST_ENVS);
-            mbar_wait<ST_WHINT>(&full[b], (it >> 1) & 1);
+            mbar_wait<ST_WHINT>(&full[b], (it / ST_TILES) & 1);
             // ---- raw observations: one TMA bulk store of the whole tile (manual copy for odd tails / pitched rows) ----
             const bool bulk = a.obs_vec && ((rows & 1) == 0);     // rows * 3736 B is a multiple of 16 for even rows
             if (bulk) {
@@ -440,8 +443,8 @@ __global__ void __maxnreg__(ST_MAXREG) step_fused_kernel(const StepArgs a) {   /
     }
 }
 
-constexpr size_t ST_SMEM = (size_t)(2 * ST_ENVS * OBS_W + ST_CWARPS * ST_WBUF_F) * sizeof(float) + 2 * ST_CWARPS * sizeof(EnvPlan) +
-                           8 * sizeof(uint64_t);
+constexpr size_t ST_SMEM = (size_t)(ST_TILES * ST_ENVS * OBS_W + ST_CWARPS * ST_WBUF_F) * sizeof(float) + 2 * ST_CWARPS * sizeof(EnvPlan) +
+                           (2 * ST_TILES + 4) * sizeof(uint64_t);
 static_assert(sizeof(EnvPlan) == 48 && ST_CWARPS <= 32, "plan record layout");
 
 }  // namespace phc
