@@ -9,33 +9,36 @@
 // warm-up multiplied by prod(gamma*lambda*nnt) <= (gamma*lambda)^K, which the host chooses below 2^-40, far
 // under fp32 resolution (and exactly 0 after any done), so the chunk starts from the exact carry and the
 // output is bit-identical to the serial scan; chunks whose window reaches the end of the array are exact by
-// construction.  Tiles are staged in shared memory with coalesced loads/stores (stride-33 padding).
+// construction.  Tiles are staged in shared memory with coalesced loads/stores (stride-(CH+1) padding).
 // Serial kernel: one thread, used when gamma*lambda is too close to 1 for a bounded window.
 #include "phc_common.cuh"
 
 namespace phc {
 
-constexpr int GAE_CH = 32;          // elements per thread
-constexpr int GAE_THREADS = 64;     // threads per CTA -> 2048-element tiles
-constexpr int GAE_TILE = GAE_CH * GAE_THREADS;
+constexpr int GAE_THREADS = 64;     // threads per CTA
 constexpr int GAE_KMAX = 2048;
 
-__device__ __forceinline__ int pad33(int i) { return i + (i >> 5); }
+// one padding word per CH elements: thread t starts at (CH+1)*t, and CH+1 is odd, so a warp hits 32 distinct banks
+template <int CH> __device__ __forceinline__ int padc(int i) { return i + i / CH; }
 
+// GAE_CH = elements owned by a thread.  8 for short warm-up windows (4x more threads: the kernel is latency-bound at
+// rollout sizes), 32 when the window is long (keeps the redundant warm-up work at K/32 per element).
+template <int GAE_CH>
 __global__ void __launch_bounds__(GAE_THREADS) gae_blocked_kernel(const float* __restrict__ dones, const float* __restrict__ values,
                                                                   const float* __restrict__ rewards, int64_t L, float gamma,
                                                                   float gl, int K, float* __restrict__ adv) {
     extern __shared__ float sm[];
+    constexpr int GAE_TILE = GAE_CH * GAE_THREADS;
     const int span = GAE_TILE + K + 1;                 // elements [tile0, tile0 + span) are needed
-    const int pspan = pad33(span) + 1;
+    const int pspan = padc<GAE_CH>(span) + 1;
     float* s_d = sm;
     float* s_v = s_d + pspan;
     float* s_r = s_v + pspan;
-    float* s_a = s_r + pspan;                          // [pad33(GAE_TILE)+1]
+    float* s_a = s_r + pspan;                          // [padc<GAE_CH>(GAE_TILE)+1]
     const int64_t tile0 = (int64_t)blockIdx.x * GAE_TILE;
     const int64_t avail = (L - tile0 < span) ? (L - tile0) : span;
     for (int i = threadIdx.x; i < avail; i += GAE_THREADS) {
-        const int p = pad33(i);
+        const int p = padc<GAE_CH>(i);
         s_d[p] = __ldg(dones + tile0 + i);
         s_v[p] = __ldg(values + tile0 + i);
         s_r[p] = __ldg(rewards + tile0 + i);
@@ -48,17 +51,17 @@ __global__ void __launch_bounds__(GAE_THREADS) gae_blocked_kernel(const float* _
         if (hi > L - 2) hi = L - 2;
         float last = 0.0f;
         for (int i = (int)(hi - tile0); i >= c0; --i) {
-            const int pn = pad33(i + 1), pc = pad33(i);
+            const int pn = padc<GAE_CH>(i + 1), pc = padc<GAE_CH>(i);
             const float nnt = 1.0f - s_d[pn];
             const float delta = (s_r[pn] + (gamma * s_v[pn]) * nnt) - s_v[pc];
             last = delta + (gl * nnt) * last;
             if (i < c0 + GAE_CH) s_a[pc] = last;
         }
-        if (tile0 + c0 + GAE_CH > L - 1 && tile0 + c0 <= L - 1) s_a[pad33((int)(L - 1 - tile0))] = 0.0f;
+        if (tile0 + c0 + GAE_CH > L - 1 && tile0 + c0 <= L - 1) s_a[padc<GAE_CH>((int)(L - 1 - tile0))] = 0.0f;
     }
     __syncthreads();
     const int64_t nout = (L - tile0 < GAE_TILE) ? (L - tile0) : GAE_TILE;
-    for (int i = threadIdx.x; i < nout; i += GAE_THREADS) adv[tile0 + i] = s_a[pad33(i)];
+    for (int i = threadIdx.x; i < nout; i += GAE_THREADS) adv[tile0 + i] = s_a[padc<GAE_CH>(i)];
 }
 
 // one warp: coalesced staging of 1024-element chunks, lane 0 runs the recurrence.
@@ -109,6 +112,7 @@ extern "C" int phc_gae(const float* dones, const float* values, const float* rew
     // warm-up window: (|gl|)^K <= 2^-40
     int K = -1;
     const float agl = fabsf(gl);
+    constexpr int GAE_CH = 32;                            // K is kept a multiple of 32 (shared-memory padding period)
     if (agl == 0.0f) K = GAE_CH;
     else if (agl < 1.0f) {
         const double k = 40.0 * 0.6931471805599453 / -log((double)agl);
@@ -119,15 +123,21 @@ extern "C" int phc_gae(const float* dones, const float* values, const float* rew
         gae_serial_kernel<<<1, 32, 0, s>>>(dones, values, rewards, L, gamma, gl, advantages);
         return check_launch(fn);
     }
-    const int span = GAE_TILE + K + 1;
-    const size_t smem = (size_t)(3 * ((span + (span >> 5)) + 1) + (GAE_TILE + (GAE_TILE >> 5)) + 1) * sizeof(float);
-    static thread_local size_t configured = 0;
-    if (smem > 48 * 1024 && smem > configured) {
-        cudaError_t e = cudaFuncSetAttribute(gae_blocked_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return fail((int)e, "%s: cudaFuncSetAttribute: %s", fn, cudaGetErrorString(e));
-        configured = smem;
+    const int ch = (K <= 64) ? 8 : 32;
+    const int tile = ch * GAE_THREADS;
+    const int span = tile + K + 1;
+    const size_t smem = (size_t)(3 * ((span + span / ch) + 1) + (tile + tile / ch) + 1) * sizeof(float);
+    const int64_t tiles = (L + tile - 1) / tile;
+    if (ch == 8) {
+        gae_blocked_kernel<8><<<(unsigned)tiles, GAE_THREADS, smem, s>>>(dones, values, rewards, L, gamma, gl, K, advantages);
+    } else {
+        static thread_local size_t configured = 0;
+        if (smem > 48 * 1024 && smem > configured) {
+            cudaError_t e = cudaFuncSetAttribute(gae_blocked_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e != cudaSuccess) return fail((int)e, "%s: cudaFuncSetAttribute: %s", fn, cudaGetErrorString(e));
+            configured = smem;
+        }
+        gae_blocked_kernel<32><<<(unsigned)tiles, GAE_THREADS, smem, s>>>(dones, values, rewards, L, gamma, gl, K, advantages);
     }
-    const int64_t tiles = (L + GAE_TILE - 1) / GAE_TILE;
-    gae_blocked_kernel<<<(unsigned)tiles, GAE_THREADS, smem, s>>>(dones, values, rewards, L, gamma, gl, K, advantages);
     return check_launch(fn);
 }

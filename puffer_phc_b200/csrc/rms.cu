@@ -71,15 +71,34 @@ __global__ void __launch_bounds__(RMS_THREADS) rms_moments_kernel(const float* _
     p[C + c] = q;
 }
 
-// moments[1 + i] += sum_p partial[p][i] for i in [0, 2C), fixed order; moments[0] += rows.
-__global__ void rms_reduce_kernel(const double* __restrict__ partial, int P, int64_t rows, int C, double* __restrict__ moments) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+// moments[1 + i] += sum_p partial[p][i] for i in [0, 2C); moments[0] += rows.  Deterministic: a block owns 32
+// columns, its 8 warps each sum a fixed stride-8 subset of the P partial rows (4 independent loads in flight),
+// and the 8 sub-sums are combined in a fixed order.
+__global__ void __launch_bounds__(256) rms_reduce_kernel(const double* __restrict__ partial, int P, int64_t rows, int C,
+                                                         double* __restrict__ moments) {
+    __shared__ double sh[8][33];
+    const int lane = threadIdx.x & 31, g = threadIdx.x >> 5;
+    const int i = blockIdx.x * 32 + lane;
+    double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
     if (i < 2 * C) {
-        double s = 0.0;
-        for (int p = 0; p < P; ++p) s += partial[(int64_t)p * 2 * C + i];
+        int p = g;
+        for (; p + 24 < P; p += 32) {
+            s0 += partial[(int64_t)p * 2 * C + i];
+            s1 += partial[(int64_t)(p + 8) * 2 * C + i];
+            s2 += partial[(int64_t)(p + 16) * 2 * C + i];
+            s3 += partial[(int64_t)(p + 24) * 2 * C + i];
+        }
+        for (; p < P; p += 8) s0 += partial[(int64_t)p * 2 * C + i];
+    }
+    sh[g][lane] = (s0 + s1) + (s2 + s3);
+    __syncthreads();
+    if (g == 0 && i < 2 * C) {
+        double s = sh[0][lane];
+#pragma unroll
+        for (int k = 1; k < 8; ++k) s += sh[k][lane];
         moments[1 + i] += s;
     }
-    if (i == 0) moments[0] += (double)rows;
+    if (blockIdx.x == 0 && threadIdx.x == 0) moments[0] += (double)rows;
 }
 
 // running_norm.py:26-34 on the accumulated moments; a single block so that count is read before it is bumped.
@@ -151,7 +170,7 @@ extern "C" int phc_rms_moments(const float* x, int64_t x_stride, int64_t B, int 
     rms_moments_kernel<<<grid, RMS_THREADS, 0, s>>>(x, x_stride, B, C, rows_per_block, scratch);
     int rc = check_launch(fn);
     if (rc) return rc;
-    rms_reduce_kernel<<<(2 * C + 255) / 256, 256, 0, s>>>(scratch, (int)row_blocks, B, C, moments);
+    rms_reduce_kernel<<<(2 * C + 31) / 32, 256, 0, s>>>(scratch, (int)row_blocks, B, C, moments);
     return check_launch(fn);
 }
 
@@ -160,7 +179,7 @@ extern "C" int phc_rms_reduce_partials(const double* partials, int num_partials,
     const char* fn = "phc_rms_reduce_partials";
     PHC_REQUIRE(partials && moments, PHC_EINVAL, "%s: NULL pointer", fn);
     PHC_REQUIRE(num_partials >= 0 && rows >= 0 && C >= 1, PHC_EINVAL, "%s: bad size", fn);
-    rms_reduce_kernel<<<(2 * C + 255) / 256, 256, 0, (cudaStream_t)stream>>>(partials, num_partials, rows, C, moments);
+    rms_reduce_kernel<<<(2 * C + 31) / 32, 256, 0, (cudaStream_t)stream>>>(partials, num_partials, rows, C, moments);
     return check_launch(fn);
 }
 
