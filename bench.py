@@ -205,7 +205,9 @@ def main():
     T = synth.make_motion_library(NUM_CLIPS, seed=0, device=dev)
     lib = MotionLibSMPL.from_tables(T, device=dev)           # packs the 1248-byte frame records
     rms = RunningNorm(934).to(dev)
-    fs = FusedStep(lib, N, StepConfig(), rms=rms, normalize=True, accumulate_moments=True)
+    # (PHC_BENCH_NORM / PHC_BENCH_MOM = 0 are tuning knobs only: they drop work from the step and mark the line invalid)
+    knob_norm, knob_mom = os.environ.get("PHC_BENCH_NORM", "1") != "0", os.environ.get("PHC_BENCH_MOM", "1") != "0"
+    fs = FusedStep(lib, N, StepConfig(), rms=rms, normalize=knob_norm, accumulate_moments=knob_mom)
     ins, outs = [], []
     for s in range(SETS):
         S = synth.make_env_state(T, N, seed=1 + rank + 100 * s)
@@ -235,7 +237,7 @@ def main():
         lo = (i % HORIZON) * N
         compute_gae_cuda(roll["dones"][lo:lo + N], roll["values"][lo:lo + N], roll["rewards"][lo:lo + N], 0.98, 0.2, out=adv[lo:lo + N])
         launches["n"] += 3
-        if (i + 1) % HORIZON == 0 or last:
+        if ((i + 1) % HORIZON == 0 or last) and knob_mom:
             rms.finalize()                             # all-reduce of the fp64 moments (N>1) + running-average update
             launches["n"] += 2                         # finalize + moments memset
 
@@ -305,6 +307,8 @@ def main():
                          "whole_step_gbs": (STEP_BYTES + GAE_BYTES_PER_ELEM) * N * K / (elapsed_ms * 1e-3) / 1e9},
             "gpu_launches": launches["n"], "clocks": clocks,
         }
+        if not (knob_norm and knob_mom):
+            line["invalid"] = "tuning run: PHC_BENCH_NORM/PHC_BENCH_MOM dropped work from the step"
         if e2e:
             line["e2e"] = e2e
         if world == 1 and not args.no_cpu_baseline:

@@ -57,6 +57,33 @@ PHC_HD void self_obs_vel_ang(const BodyState& b, float hz, float hw, float* o_ve
     put3(o_ang, rotate_z(-hz, hw, b.w));                                      // :85-89
 }
 
+// Fused-step flavours (explicit fmaf chains, see phc_math.cuh): same outputs to a few ulp.
+PHC_HD void task_obs_body_fma(const BodyState& b, const BodyState& r, V3 root_pos, float hz, float hw, const ZRot& h, float* o_dpos,
+                              float* o_drot, float* o_dvel, float* o_dang, float* o_lpos, float* o_lrot) {
+    put3(o_dpos, zrot_inv(h, r.p - b.p));                                                 // common.py:138-139
+    const Q4 dq = quat_mul_conj_fma(r.q, b.q);                                            // :142-145
+    tan_norm_fma(quat_mul_zr(quat_mul_zl(-hz, hw, dq), hz, hw), o_drot);                  // :146-149, :169
+    put3(o_dvel, zrot_inv(h, r.v - b.v));                                                 // :152-153
+    put3(o_dang, zrot_inv(h, r.w - b.w));                                                 // :155-156
+    put3(o_lpos, zrot_inv(h, r.p - root_pos));                                            // :159-162
+    tan_norm_fma(quat_mul_zl(-hz, hw, r.q), o_lrot);                                      // :164-165
+}
+PHC_HD void self_obs_pos_rot_fma(const BodyState& b, V3 root_pos, float hz, float hw, const ZRot& h, int j, float* o_pos, float* o_rot) {
+    if (j >= 1) put3(o_pos, zrot_inv(h, b.p - root_pos));                                 // common.py:57-66
+    tan_norm_fma(quat_mul_zl(-hz, hw, b.q), o_rot);                                       // :68-75
+}
+PHC_HD void self_obs_vel_ang_fma(const BodyState& b, const ZRot& h, float* o_vel, float* o_ang) {
+    put3(o_vel, zrot_inv(h, b.v));                                                        // common.py:81-83
+    put3(o_ang, zrot_inv(h, b.w));                                                        // :85-89
+}
+PHC_HD void reward_terms_body_fma(const BodyState& b, const BodyState& r, float& sp, float& sr, float& sv, float& sa) {
+    const V3 dp = r.p - b.p, dv = r.v - b.v, da = r.w - b.w;
+    sp = fmaf(dp.z, dp.z, fmaf(dp.y, dp.y, dp.x * dp.x));
+    sr = quat_angle_sq(quat_mul_conj_fma(r.q, b.q));
+    sv = fmaf(dv.z, dv.z, fmaf(dv.y, dv.y, dv.x * dv.x));
+    sa = fmaf(da.z, da.z, fmaf(da.y, da.y, da.x * da.x));
+}
+
 // compute_imitation_reward, per-body terms (common.py:298-316).
 PHC_HD void reward_terms_body(const BodyState& b, const BodyState& r, float& sp, float& sr, float& sv, float& sa) {
     sp = mean_sq3(r.p - b.p);

@@ -96,6 +96,48 @@ PHC_HD void tan_norm(Q4 q, float* o) {
     o[5] = s + (q.z * q.z) * 2.0f;
 }
 
+// ---- fused-multiply-add flavours for the fused step's observation math ----------------------------------------
+// Same quantities as quat_mul / rotate_z / tan_norm above, written as explicit fmaf chains (about half the
+// instructions).  They round differently from the reference's op-by-op sequence (a few ulp), which is fine for
+// the fp32 observation values (tolerance 1e-5) and is never used for anything that feeds an index or a flag.
+struct ZRot { float A, B, C; };     // rotation about z by the heading quaternion (0,0,qz,qw): A = cos h, B = sin h, C = 1
+PHC_HD ZRot zrot_make(float qz, float qw) {
+    ZRot r;
+    r.A = fmaf(2.0f * qw, qw, -1.0f);
+    r.B = (2.0f * qz) * qw;
+    r.C = fmaf(2.0f * qz, qz, r.A);
+    return r;
+}
+// my_quat_rotate((0,0,-qz,qw), v): the inverse heading rotation
+PHC_HD V3 zrot_inv(const ZRot& h, V3 v) { return V3{fmaf(h.B, v.y, h.A * v.x), fmaf(-h.B, v.x, h.A * v.y), h.C * v.z}; }
+// (0,0,z1,w1) * q
+PHC_HD Q4 quat_mul_zl(float z1, float w1, Q4 q) {
+    return Q4{fmaf(-z1, q.y, w1 * q.x), fmaf(z1, q.x, w1 * q.y), fmaf(z1, q.w, w1 * q.z), fmaf(-z1, q.z, w1 * q.w)};
+}
+// q * (0,0,z2,w2)
+PHC_HD Q4 quat_mul_zr(Q4 q, float z2, float w2) {
+    return Q4{fmaf(q.y, z2, q.x * w2), fmaf(-q.x, z2, q.y * w2), fmaf(q.w, z2, q.z * w2), fmaf(-q.z, z2, q.w * w2)};
+}
+// a * conj(b)
+PHC_HD Q4 quat_mul_conj_fma(Q4 a, Q4 b) {
+    Q4 r;
+    r.x = fmaf(-a.w, b.x, fmaf(a.x, b.w, fmaf(-a.y, b.z, a.z * b.y)));
+    r.y = fmaf(-a.w, b.y, fmaf(a.y, b.w, fmaf(-a.z, b.x, a.x * b.z)));
+    r.z = fmaf(-a.w, b.z, fmaf(a.z, b.w, fmaf(-a.x, b.y, a.y * b.x)));
+    r.w = fmaf(a.w, b.w, fmaf(a.x, b.x, fmaf(a.y, b.y, a.z * b.z)));
+    return r;
+}
+PHC_HD void tan_norm_fma(Q4 q, float* o) {
+    const float x2 = 2.0f * q.x, y2 = 2.0f * q.y, z2 = 2.0f * q.z;
+    const float s = fmaf(2.0f * q.w, q.w, -1.0f);
+    o[0] = fmaf(x2, q.x, s);
+    o[1] = fmaf(z2, q.w, y2 * q.x);
+    o[2] = fmaf(-y2, q.w, z2 * q.x);
+    o[3] = fmaf(y2, q.w, x2 * q.z);
+    o[4] = fmaf(-x2, q.w, y2 * q.z);
+    o[5] = fmaf(z2, q.z, s);
+}
+
 // calc_heading (torch_utils.py:369-380): atan2 of the rotated x axis.
 PHC_HD float calc_heading(Q4 q) {
     float s = 2.0f * (q.w * q.w) - 1.0f;

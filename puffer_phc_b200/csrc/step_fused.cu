@@ -18,17 +18,18 @@
 //     store (cp.async.bulk), write the RunningNorm-normalised copy and accumulate the fp64 column moments
 //     from the same tile (column-owning threads keep mean, 1/sqrt(var+eps) and the accumulators in registers),
 //     then release the tile (mbarrier).  Compute warps never wait for stores.
-//   * 1 planner warp: lane = (env slot, role).  It reads the per-env scalars (coalesced across envs), does the
-//     id -> motion-meta lookups and the frame-index / blend arithmetic (bit-exact op order) one iteration ahead and
-//     leaves a 48-byte plan per compute warp in shared memory, so compute warps never execute (32x redundantly)
-//     or wait on that dependent load chain.
+//   * 1 planner warp (runs up to three iterations ahead): lane = (env slot, role) reads the per-env
+//     scalars (coalesced across envs), does the id -> motion-meta lookups and the frame-index / blend arithmetic
+//     (bit-exact op order) and leaves a 48-byte plan per compute warp in shared memory, so compute warps never
+//     execute (32x redundantly) or wait on that dependent load chain.
+//   * Register budget: each SM sub-partition holds 16384 registers = 6 warps x 80 (the default: 16 compute + 4 writer + 1 planner warps).
 //   * Body reductions are warp shuffles; the flag-critical chain keeps the reference's fp32 op order.
 #include "phc_body.cuh"
 
 namespace phc {
 
 #ifndef ST_SLOTS
-#define ST_SLOTS 8                                   // envs per CTA iteration (multiple of 4: tiles stay 16-byte aligned)
+#define ST_SLOTS 8                                   // envs per CTA iteration (even: tiles stay 16-byte aligned)
 #endif
 constexpr int ST_ENVS = ST_SLOTS;
 constexpr int ST_CWARPS = 2 * ST_ENVS;               // compute warps
@@ -45,12 +46,14 @@ constexpr int ST_CWARPS = 2 * ST_ENVS;               // compute warps
 #define ST_WRITERS 4
 #endif
 constexpr int ST_WWARPS = ST_WRITERS;                // writer warps
-// register budget: the register file holds 20 warps x 96 registers or 21-24 warps x 80
+// register budget per SM sub-partition (16384 registers): ceil(warps / 4) x 32 x ST_MAXREG must fit
 #ifndef ST_MAXREG
-#define ST_MAXREG (((2 * ST_SLOTS + ST_WRITERS + 1) <= 20) ? 96 : 80)
+#define ST_NWARPS (2 * ST_SLOTS + ST_WRITERS + 1)
+#define ST_MAXREG ((ST_NWARPS <= 20) ? 96 : ((ST_NWARPS <= 24) ? 80 : ((ST_NWARPS <= 28) ? 72 : 64)))
 #endif
 constexpr int ST_WTHREADS = ST_WWARPS * 32;
 constexpr int ST_THREADS = (ST_CWARPS + ST_WWARPS + 1) * 32;     // + the planner warp
+constexpr int ST_PLANS = 4;                          // plan ring: plans are produced three iterations ahead
 constexpr int ST_WPAIRS = (OBS_W / 2 + ST_WTHREADS - 1) / ST_WTHREADS;  // column pairs owned by a writer thread
 constexpr int ST_DOF_F = 144;                        // dof_force (69, padded to 72) | dof_vel (69, padded to 72)
 constexpr int ST_WBUF_F = 3 * FRAME_F + ST_DOF_F;    // per compute warp: sim record | frame 0 | frame 1 | dof force/vel
@@ -211,12 +214,11 @@ __global__ void __maxnreg__(ST_MAXREG) step_fused_kernel(const StepArgs a) {   /
     extern __shared__ float4 smem4[];
     float* tiles = reinterpret_cast<float*>(smem4);                          // [ST_TILES][S][934]
     float* wbufs = tiles + ST_TILES * ST_ENVS * OBS_W;                       // [2S][3 frames + dof]
-    EnvPlan* plans = reinterpret_cast<EnvPlan*>(wbufs + ST_CWARPS * ST_WBUF_F);     // [2][2S]
-    uint64_t* bars = reinterpret_cast<uint64_t*>(plans + 2 * ST_CWARPS);
+    EnvPlan* plans = reinterpret_cast<EnvPlan*>(wbufs + ST_CWARPS * ST_WBUF_F);     // [ST_PLANS][2S]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(plans + ST_PLANS * ST_CWARPS);
     uint64_t* full = bars;                    // [ST_TILES] tile b written by all compute warps
     uint64_t* empty = bars + ST_TILES;        // [ST_TILES] tile b drained by the writers
-    uint64_t* pfull = bars + 2 * ST_TILES;    // [2] plan set d written by the planner
-    uint64_t* pempty = pfull + 2;             // [2] plan set d consumed by all compute warps
+    uint64_t* pfull = bars + 2 * ST_TILES;    // [ST_PLANS] plan set d written by the planning writer warp
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const phc_step_in& in = a.in;
@@ -225,8 +227,7 @@ __global__ void __maxnreg__(ST_MAXREG) step_fused_kernel(const StepArgs a) {   /
 
     if (tid == 0) {
         for (int i = 0; i < ST_TILES; ++i) { mbar_init(&full[i], ST_CWARPS); mbar_init(&empty[i], 1); }
-        mbar_init(&pfull[0], 1); mbar_init(&pfull[1], 1);
-        mbar_init(&pempty[0], ST_CWARPS); mbar_init(&pempty[1], ST_CWARPS);
+        for (int i = 0; i < ST_PLANS; ++i) mbar_init(&pfull[i], 1);
     }
     __syncthreads();
 
@@ -239,8 +240,6 @@ __global__ void __maxnreg__(ST_MAXREG) step_fused_kernel(const StepArgs a) {   /
         if ((int64_t)blockIdx.x < a.num_blocks) {
             mbar_wait<ST_CHINT>(&pfull[0], 0);
             cur = plans[warp];
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&pempty[0]);
             if (cur.valid) issue_env<PACKED>(a, cur, (int64_t)blockIdx.x * ST_ENVS + slot, role, wbuf, lane);
         }
         cp_async_commit();
@@ -283,11 +282,9 @@ __global__ void __maxnreg__(ST_MAXREG) step_fused_kernel(const StepArgs a) {   /
             {
                 const int64_t nblk = blk + gridDim.x;
                 if (nblk < a.num_blocks) {
-                    const int d = (it + 1) & 1;
-                    mbar_wait<ST_CHINT>(&pfull[d], ((it + 1) >> 1) & 1);
+                    const int d = (it + 1) % ST_PLANS;
+                    mbar_wait<ST_CHINT>(&pfull[d], ((it + 1) / ST_PLANS) & 1);
                     nxt = plans[d * ST_CWARPS + warp];
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(&pempty[d]);
                     if (nxt.valid) issue_env<PACKED>(a, nxt, nblk * ST_ENVS + slot, role, wbuf, lane);
                 }
                 cp_async_commit();
@@ -297,13 +294,14 @@ __global__ void __maxnreg__(ST_MAXREG) step_fused_kernel(const StepArgs a) {   /
             if (valid) {
                 float hz, hw;
                 heading_quat_direct(root_q, hz, hw);                           // upright start: no base-rot removal
+                const ZRot hrot = zrot_make(hz, hw);
                 if (role == 0) {
                     // ============ role A: reward, reset, power, self observation (reference at t) ============
                     float sp = 0.0f, sr = 0.0f, sv = 0.0f, sa = 0.0f, dist = 0.0f;
                     bool over = false;
                     const bool in_mask = lane < NB && ((cfg.reset_body_mask >> lane) & 1u);
                     if (lane < NB) {
-                        reward_terms_body_fast(body, ref, sp, sr, sv, sa);
+                        reward_terms_body_fma(body, ref, sp, sr, sv, sa);
                         if (in_mask) {
                             dist = norm3(body.p - ref.p);
                             over = dist > __ldg(in.term_dist + j);
@@ -311,7 +309,7 @@ __global__ void __maxnreg__(ST_MAXREG) step_fused_kernel(const StepArgs a) {   /
                         if (out.ref_state_t) store_ref(out.ref_state_t + e * FRAME_F, j, ref);
                         float* o = my_tile;
                         if (j == 0) o[0] = root_p.z;                                      // common.py:40
-                        self_obs_pos_rot(body, root_p, hz, hw, j, o + 1 + 3 * (j - 1), o + 70 + 6 * j);   // vel / ang blocks: role B
+                        self_obs_pos_rot_fma(body, root_p, hz, hw, hrot, j, o + 1 + 3 * (j - 1), o + 70 + 6 * j);   // vel / ang blocks: role B
                     }
                     sp = warp_sum(sp); sr = warp_sum(sr); sv = warp_sum(sv); sa = warp_sum(sa);
                     bool fallen = false;
@@ -344,9 +342,9 @@ __global__ void __maxnreg__(ST_MAXREG) step_fused_kernel(const StepArgs a) {   /
                 } else if (lane < NB) {
                     // ============ role B: imitation observation (reference at t+1) ============================
                     if (out.ref_state_t1) store_ref(out.ref_state_t1 + e * FRAME_F, j, ref);
-                    self_obs_vel_ang(body, hz, hw, my_tile + 214 + 3 * j, my_tile + 286 + 3 * j);      // balances the two roles
+                    self_obs_vel_ang_fma(body, hrot, my_tile + 214 + 3 * j, my_tile + 286 + 3 * j);      // balances the two roles
                     float* q = my_tile + OBS_SELF;
-                    task_obs_body(body, ref, root_p, hz, hw, q + 3 * j, q + 72 + 6 * j, q + 216 + 3 * j, q + 288 + 3 * j,
+                    task_obs_body_fma(body, ref, root_p, hz, hw, hrot, q + 3 * j, q + 72 + 6 * j, q + 216 + 3 * j, q + 288 + 3 * j,
                                   q + 360 + 3 * j, q + 432 + 6 * j);
                 }
             }
@@ -432,10 +430,16 @@ __global__ void __maxnreg__(ST_MAXREG) step_fused_kernel(const StepArgs a) {   /
         }
     } else {
         // ====================================== planner warp =======================================
-        int it = 0;
-        for (int64_t blk = blockIdx.x; blk < a.num_blocks; blk += gridDim.x, ++it) {
-            const int d = it & 1;
-            if (it >= 2) mbar_wait<ST_WHINT>(&pempty[d], ((it >> 1) - 1) & 1);
+        // Plan p may overwrite ring slot p % 4 (last used by plan p - 4) once full[p - 3] has completed: every compute warp
+        // that finished iteration p - 3 has consumed plan p - 2 already.  The compute warps cannot complete iteration p - 1
+        // without plan p, so the tile barrier polled here never runs a full phase ahead of this warp.
+        int p = 0;
+        for (int64_t blk = blockIdx.x; blk < a.num_blocks; blk += gridDim.x, ++p) {
+            if (p >= ST_PLANS - 1) {
+                const int q = p - (ST_PLANS - 1);
+                mbar_wait<ST_WHINT>(&full[q % ST_TILES], (q / ST_TILES) & 1);
+            }
+            const int d = p % ST_PLANS;
             if (lane < ST_CWARPS) plans[d * ST_CWARPS + lane] = make_plan(a, blk * ST_ENVS + lane % ST_ENVS, lane / ST_ENVS);
             __syncwarp();
             if (lane == 0) mbar_arrive(&pfull[d]);
@@ -443,8 +447,8 @@ __global__ void __maxnreg__(ST_MAXREG) step_fused_kernel(const StepArgs a) {   /
     }
 }
 
-constexpr size_t ST_SMEM = (size_t)(ST_TILES * ST_ENVS * OBS_W + ST_CWARPS * ST_WBUF_F) * sizeof(float) + 2 * ST_CWARPS * sizeof(EnvPlan) +
-                           (2 * ST_TILES + 4) * sizeof(uint64_t);
+constexpr size_t ST_SMEM = (size_t)(ST_TILES * ST_ENVS * OBS_W + ST_CWARPS * ST_WBUF_F) * sizeof(float) + ST_PLANS * ST_CWARPS * sizeof(EnvPlan) +
+                           (2 * ST_TILES + ST_PLANS) * sizeof(uint64_t);
 static_assert(sizeof(EnvPlan) == 48 && ST_CWARPS <= 32, "plan record layout");
 
 }  // namespace phc

@@ -47,6 +47,7 @@ extern "C" int harness_step(const phc_motion_tables* T, const phc_step_in* in, c
         const V3 root_p{sim[0], sim[1], sim[2]};
         float hz, hw;
         heading_quat_direct(root_q, hz, hw);
+        const ZRot hrot = zrot_make(hz, hw);
         float sp[32] = {0}, sr[32] = {0}, sv[32] = {0}, sa[32] = {0}, dist[32] = {0};
         bool over = false;
         float* tile = out->obs + e * out->obs_stride;
@@ -54,16 +55,17 @@ extern "C" int harness_step(const phc_motion_tables* T, const phc_step_in* in, c
             const float* sj = sim + REC * j;
             const BodyState body{V3{sj[0], sj[1], sj[2]}, Q4{sj[3], sj[4], sj[5], sj[6]}, V3{sj[7], sj[8], sj[9]}, V3{sj[10], sj[11], sj[12]}};
             const BodyState r0 = blend_frames(frame(T, a0 + ls, j), frame(T, a1 + ls, j), bla, off);
-            reward_terms_body_fast(body, r0, sp[j], sr[j], sv[j], sa[j]);
+            reward_terms_body_fma(body, r0, sp[j], sr[j], sv[j], sa[j]);
             if ((cfg->reset_body_mask >> j) & 1u) {
                 dist[j] = norm3(body.p - r0.p);
                 over = over || (dist[j] > in->term_dist[j]);
             }
             const BodyState r1 = blend_frames(frame(T, b0 + ls, j), frame(T, b1 + ls, j), blb, off);
             if (j == 0) tile[0] = root_p.z;
-            self_obs_body(body, root_p, hz, hw, j, tile + 1 + 3 * (j - 1), tile + 70 + 6 * j, tile + 214 + 3 * j, tile + 286 + 3 * j);
+            self_obs_pos_rot_fma(body, root_p, hz, hw, hrot, j, tile + 1 + 3 * (j - 1), tile + 70 + 6 * j);
+            self_obs_vel_ang_fma(body, hrot, tile + 214 + 3 * j, tile + 286 + 3 * j);
             float* q = tile + OBS_SELF;
-            task_obs_body(body, r1, root_p, hz, hw, q + 3 * j, q + 72 + 6 * j, q + 216 + 3 * j, q + 288 + 3 * j, q + 360 + 3 * j, q + 432 + 6 * j);
+            task_obs_body_fma(body, r1, root_p, hz, hw, hrot, q + 3 * j, q + 72 + 6 * j, q + 216 + 3 * j, q + 288 + 3 * j, q + 360 + 3 * j, q + 432 + 6 * j);
         }
         bool fallen = false;
         if (cfg->enable_early_termination) {
