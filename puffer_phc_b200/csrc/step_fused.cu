@@ -6,33 +6,38 @@
 // RunningNorm.update needs (policies/running_norm.py:15-34).
 //
 // Design (persistent, warp-specialised, one CTA per SM):
-//   * 2*S compute warps: each iteration the CTA owns S consecutive envs and TWO warps work on each env,
-//     lane j = body j:   role A: reference at t   -> reward terms, termination test, power term, self obs
-//                        role B: reference at t+1 -> imitation (task) observation
-//     Every compute warp owns a private 3 x 1248 B shared-memory buffer (PhysX record + its two bracketing
-//     reference frames).  The NEXT env's record and frames are fetched with cp.async right after the current
-//     ones have been read into registers, so the gathers fly during ~800 instructions of math and never
-//     occupy registers (the kernel is latency-bound, not bandwidth-bound, without this).
+//   * compute groups: each iteration the CTA owns S consecutive envs.  A group of THREE warps works on FOUR envs
+//     (4 x 24 bodies = 96 lanes: every lane carries one body, no idle lanes) and there are two groups per four envs:
+//         role A: reference at t   -> reward terms, termination test, power term, self observation (pos / rot)
+//         role B: reference at t+1 -> imitation (task) observation, self observation (vel / ang-vel)
+//     Every (env, role) owns a private shared-memory buffer (PhysX record | frame 0 | frame 1 | dof force/vel).  The
+//     NEXT env's record and frames are fetched with cp.async right after the current ones have been read into
+//     registers, so the gathers fly behind ~700 instructions of math and never occupy registers (without this the
+//     kernel is latency-bound, not bandwidth-bound).  Per-env reductions (24 bodies spread over two warps) go
+//     through shared memory in a fixed order (deterministic).
 //   * 4 writer warps: the S x 934-float observation tile is double-buffered in shared memory.  When a tile is
 //     full (mbarrier) the writers send it to HBM as ONE contiguous 16-byte aligned block with a TMA bulk
 //     store (cp.async.bulk), write the RunningNorm-normalised copy and accumulate the fp64 column moments
-//     from the same tile (column-owning threads keep mean, 1/sqrt(var+eps) and the accumulators in registers),
+//     from the same tile (column-pair-owning threads keep mean, 1/sqrt(var+eps) and the accumulators in registers),
 //     then release the tile (mbarrier).  Compute warps never wait for stores.
 //   * 1 planner warp (runs up to three iterations ahead): lane = (env slot, role) reads the per-env
 //     scalars (coalesced across envs), does the id -> motion-meta lookups and the frame-index / blend arithmetic
-//     (bit-exact op order) and leaves a 48-byte plan per compute warp in shared memory, so compute warps never
+//     (bit-exact op order) and leaves a 48-byte plan per (env, role) in shared memory, so compute warps never
 //     execute (32x redundantly) or wait on that dependent load chain.
-//   * Register budget: each SM sub-partition holds 16384 registers = 6 warps x 80 (the default: 16 compute + 4 writer + 1 planner warps).
-//   * Body reductions are warp shuffles; the flag-critical chain keeps the reference's fp32 op order.
+//   * Register budget: each SM sub-partition holds 16384 registers = 5 warps x 96 or 6 warps x 80 (default S = 8: 12 compute + 4 writer
+//     + 1 planner warps).  The flag-critical chain keeps the reference's fp32 op order.
 #include "phc_body.cuh"
 
 namespace phc {
 
 #ifndef ST_SLOTS
-#define ST_SLOTS 8                                   // envs per CTA iteration (even: tiles stay 16-byte aligned)
+#define ST_SLOTS 8                                   // envs per CTA iteration (multiple of 4: one compute group = 4 envs)
 #endif
 constexpr int ST_ENVS = ST_SLOTS;
-constexpr int ST_CWARPS = 2 * ST_ENVS;               // compute warps
+constexpr int ST_GROUPS = ST_ENVS / 4;               // compute groups per role
+constexpr int ST_CWARPS = 2 * 3 * ST_GROUPS;         // compute warps: 3 warps per group, 2 roles
+constexpr int ST_NBUF = 2 * ST_ENVS;                 // staging buffers / plans per iteration: (role, slot)
+static_assert(ST_ENVS % 4 == 0 && ST_NBUF <= 32, "a compute group handles 4 envs; the planner has one lane per buffer");
 #ifndef ST_CHINT
 #define ST_CHINT 0
 #endif
@@ -42,13 +47,16 @@ constexpr int ST_CWARPS = 2 * ST_ENVS;               // compute warps
 #ifndef ST_TILES
 #define ST_TILES 2                                   // observation tiles in flight between compute and writer warps
 #endif
+#ifndef ST_WUNROLL
+#define ST_WUNROLL 1
+#endif
 #ifndef ST_WRITERS
 #define ST_WRITERS 4
 #endif
 constexpr int ST_WWARPS = ST_WRITERS;                // writer warps
 // register budget per SM sub-partition (16384 registers): ceil(warps / 4) x 32 x ST_MAXREG must fit
 #ifndef ST_MAXREG
-#define ST_NWARPS (2 * ST_SLOTS + ST_WRITERS + 1)
+#define ST_NWARPS (6 * (ST_SLOTS / 4) + ST_WRITERS + 1)
 #define ST_MAXREG ((ST_NWARPS <= 20) ? 96 : ((ST_NWARPS <= 24) ? 80 : ((ST_NWARPS <= 28) ? 72 : 64)))
 #endif
 constexpr int ST_WTHREADS = ST_WWARPS * 32;
@@ -107,6 +115,8 @@ __device__ __forceinline__ void bulk_store(void* gdst, const void* smem_src, uns
 }
 __device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+// named barriers 2.. : one per compute group (3 warps = 96 threads)
+__device__ __forceinline__ void group_sync(int id) { asm volatile("bar.sync %0, 96;" ::"r"(id) : "memory"); }
 __device__ __forceinline__ void writers_sync() { asm volatile("bar.sync 1, %0;" ::"n"(ST_WTHREADS) : "memory"); }
 // torch.clamp propagates NaN: min.NaN / max.NaN do too (fminf / fmaxf would drop it)
 __device__ __forceinline__ float clamp_nan(float y, float lim) {
@@ -152,12 +162,13 @@ __device__ __forceinline__ EnvPlan make_plan(const StepArgs& a, int64_t e, int r
     return p;
 }
 
-// Stage one reference frame (pos 72 | rot 96 | vel 72 | ang 72 floats) into shared memory: 78 x 16-byte chunks.
+// Stage one reference frame (pos 72 | rot 96 | vel 72 | ang 72 floats) into shared memory: 78 x 16-byte chunks,
+// issued by the 24 lanes (j = body index) that work on this env.
 template <bool PACKED>
-__device__ __forceinline__ void stage_frame(const phc_motion_tables& T, int64_t f, float* dst, int lane) {
+__device__ __forceinline__ void stage_frame(const phc_motion_tables& T, int64_t f, float* dst, int j) {
 #pragma unroll
-    for (int k = 0; k < 3; ++k) {
-        const int i = lane + 32 * k;
+    for (int k = 0; k < 4; ++k) {
+        const int i = j + NB * k;
         if (i < FRAME_F / 4) {
             const float* src;
             if (PACKED) src = T.packed + f * FRAME_F + 4 * i;
@@ -170,26 +181,27 @@ __device__ __forceinline__ void stage_frame(const phc_motion_tables& T, int64_t 
     }
 }
 
-// Async fetch of everything a compute warp reads for env e: PhysX record, its two frames, (role A) dof force / vel.
+// Async fetch of everything the 24 lanes of (env e, role) read: PhysX record, two frames, (role A) dof force / vel.
 template <bool PACKED>
-__device__ __forceinline__ void issue_env(const StepArgs& a, const EnvPlan& p, int64_t e, int role, float* wbuf, int lane) {
+__device__ __forceinline__ void issue_env(const StepArgs& a, const EnvPlan& p, int64_t e, int role, float* wbuf, int j) {
     const phc_step_in& in = a.in;
     const float* rec = in.body_state + e * in.env_stride;
     if (a.sim_vec) {
 #pragma unroll
-        for (int k = 0; k < 3; ++k) {
-            const int i = lane + 32 * k;
+        for (int k = 0; k < 4; ++k) {
+            const int i = j + NB * k;
             if (i < SIM_F / 4) cp_async16(wbuf + 4 * i, rec + 4 * i);
         }
     } else {
-        for (int i = lane; i < SIM_F; i += 32) cp_async4(wbuf + i, rec + i);
+#pragma unroll
+        for (int k = 0; k < REC; ++k) cp_async4(wbuf + j + NB * k, rec + j + NB * k);
     }
-    stage_frame<PACKED>(a.t, p.f0, wbuf + FRAME_F, lane);
-    if (p.f1 != p.f0) stage_frame<PACKED>(a.t, p.f1, wbuf + 2 * FRAME_F, lane);
+    stage_frame<PACKED>(a.t, p.f0, wbuf + FRAME_F, j);
+    if (p.f1 != p.f0) stage_frame<PACKED>(a.t, p.f1, wbuf + 2 * FRAME_F, j);
     if (role == 0 && in.dof_force) {
 #pragma unroll
         for (int k = 0; k < 3; ++k) {
-            const int c = lane + 32 * k;
+            const int c = j + NB * k;
             if (c < NDOF) {
                 cp_async4(wbuf + 3 * FRAME_F + c, in.dof_force + e * NDOF + c);
                 cp_async4(wbuf + 3 * FRAME_F + 72 + c, in.dof_vel + e * NDOF + c);
@@ -213,9 +225,11 @@ template <bool PACKED>
 __global__ void __maxnreg__(ST_MAXREG) step_fused_kernel(const StepArgs a) {   // one persistent CTA per SM
     extern __shared__ float4 smem4[];
     float* tiles = reinterpret_cast<float*>(smem4);                          // [ST_TILES][S][934]
-    float* wbufs = tiles + ST_TILES * ST_ENVS * OBS_W;                       // [2S][3 frames + dof]
-    EnvPlan* plans = reinterpret_cast<EnvPlan*>(wbufs + ST_CWARPS * ST_WBUF_F);     // [ST_PLANS][2S]
-    uint64_t* bars = reinterpret_cast<uint64_t*>(plans + ST_PLANS * ST_CWARPS);
+    float* wbufs = tiles + ST_TILES * ST_ENVS * OBS_W;                       // [2][S][record | frame 0 | frame 1 | dof]
+    float* red = wbufs + ST_NBUF * ST_WBUF_F;                                // [S][24][8]  per-body partials (role A)
+    float* red2 = red + ST_ENVS * NB * 8;                                    // [S][6][4]   second-stage partial sums
+    EnvPlan* plans = reinterpret_cast<EnvPlan*>(red2 + ST_ENVS * 24);        // [ST_PLANS][2S]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(plans + ST_PLANS * ST_NBUF);
     uint64_t* full = bars;                    // [ST_TILES] tile b written by all compute warps
     uint64_t* empty = bars + ST_TILES;        // [ST_TILES] tile b drained by the writers
     uint64_t* pfull = bars + 2 * ST_TILES;    // [ST_PLANS] plan set d written by the planning writer warp
@@ -233,14 +247,18 @@ __global__ void __maxnreg__(ST_MAXREG) step_fused_kernel(const StepArgs a) {   /
 
     if (warp < ST_CWARPS) {
         // ====================================== compute warps ======================================
-        const int role = warp / ST_ENVS, slot = warp % ST_ENVS;
-        float* wbuf = wbufs + warp * ST_WBUF_F;
-        const int j = lane;
+        // group = 3 warps = 96 lanes = 4 envs x 24 bodies; lane t of the group works on body t % 24 of env slot 4g + t / 24
+        const int role = warp / (3 * ST_GROUPS), gw = warp % (3 * ST_GROUPS);
+        const int g = gw / 3, t = (gw % 3) * 32 + lane;
+        const int el = t / NB, j = t % NB;
+        const int slot = 4 * g + el, buf = role * ST_ENVS + slot;
+        const int bar_id = 2 + role * ST_GROUPS + g;
+        float* wbuf = wbufs + buf * ST_WBUF_F;
         EnvPlan cur{};
         if ((int64_t)blockIdx.x < a.num_blocks) {
             mbar_wait<ST_CHINT>(&pfull[0], 0);
-            cur = plans[warp];
-            if (cur.valid) issue_env<PACKED>(a, cur, (int64_t)blockIdx.x * ST_ENVS + slot, role, wbuf, lane);
+            cur = plans[buf];
+            if (cur.valid) issue_env<PACKED>(a, cur, (int64_t)blockIdx.x * ST_ENVS + slot, role, wbuf, j);
         }
         cp_async_commit();
         int it = 0;
@@ -250,9 +268,9 @@ __global__ void __maxnreg__(ST_MAXREG) step_fused_kernel(const StepArgs a) {   /
             const int b = it % ST_TILES, use = it / ST_TILES;                  // use-th time tile buffer b is filled
             float* my_tile = tiles + (b * ST_ENVS + slot) * OBS_W;
 
-            // ---- operands of this env: shared memory -> registers, blend the two frames ----------------
+            // ---- operands of this body: shared memory -> registers, blend the two frames ----------------
             cp_async_wait_all();
-            __syncwarp();
+            group_sync(bar_id);                                                // the copies of all 96 lanes have landed
             BodyState body{}, ref{};
             V3 root_p{};
             Q4 root_q{0.0f, 0.0f, 0.0f, 1.0f};
@@ -260,93 +278,99 @@ __global__ void __maxnreg__(ST_MAXREG) step_fused_kernel(const StepArgs a) {   /
             if (valid) {
                 root_p = ld3(wbuf);
                 root_q = ld4(wbuf + 3);
-                if (lane < NB) {
-                    const float* sj = wbuf + REC * j;
-                    body = BodyState{ld3(sj), ld4(sj + 3), ld3(sj + 7), ld3(sj + 10)};
-                    const BodyState F0 = read_frame(wbuf + FRAME_F, j);
-                    const BodyState F1 = (cur.f1 == cur.f0) ? F0 : read_frame(wbuf + 2 * FRAME_F, j);
-                    ref = blend_frames(F0, F1, cur.blend, V3{cur.offx, cur.offy, cur.offz});
-                }
-                if (role == 0 && in.dof_force) {                                  // humanoid_phc.py:1295-1303
-                    const float* df = wbuf + 3 * FRAME_F;
-#pragma unroll
-                    for (int k = 0; k < 3; ++k) {
-                        const int c = lane + 32 * k;
-                        if (c < NDOF) power = power + fabsf(df[c] * df[72 + c]);
-                    }
+                const float* sj = wbuf + REC * j;
+                body = BodyState{ld3(sj), ld4(sj + 3), ld3(sj + 7), ld3(sj + 10)};
+                const BodyState F0 = read_frame(wbuf + FRAME_F, j);
+                const BodyState F1 = (cur.f1 == cur.f0) ? F0 : read_frame(wbuf + 2 * FRAME_F, j);
+                ref = blend_frames(F0, F1, cur.blend, V3{cur.offx, cur.offy, cur.offz});
+                if (role == 0 && in.dof_force && j < 23) {                         // humanoid_phc.py:1295-1303
+                    const float* df = wbuf + 3 * FRAME_F + 3 * j;
+                    power = (fabsf(df[0] * df[72]) + fabsf(df[1] * df[73])) + fabsf(df[2] * df[74]);
                 }
             }
-            __syncwarp();
-            // ---- the buffer is free again: fetch the next env's record and frames behind the math ----------
+            group_sync(bar_id);                                                // everyone has read: the buffers are free again
+            // ---- fetch the next env's record and frames behind the math -----------------------------------
             EnvPlan nxt{};
             {
                 const int64_t nblk = blk + gridDim.x;
                 if (nblk < a.num_blocks) {
                     const int d = (it + 1) % ST_PLANS;
                     mbar_wait<ST_CHINT>(&pfull[d], ((it + 1) / ST_PLANS) & 1);
-                    nxt = plans[d * ST_CWARPS + warp];
-                    if (nxt.valid) issue_env<PACKED>(a, nxt, nblk * ST_ENVS + slot, role, wbuf, lane);
+                    nxt = plans[d * ST_NBUF + buf];
+                    if (nxt.valid) issue_env<PACKED>(a, nxt, nblk * ST_ENVS + slot, role, wbuf, j);
                 }
                 cp_async_commit();
             }
             if (use >= 1) mbar_wait<ST_CHINT>(&empty[b], (use - 1) & 1);               // tile buffer b released by the writers
 
-            if (valid) {
-                float hz, hw;
-                heading_quat_direct(root_q, hz, hw);                           // upright start: no base-rot removal
-                const ZRot hrot = zrot_make(hz, hw);
-                if (role == 0) {
-                    // ============ role A: reward, reset, power, self observation (reference at t) ============
-                    float sp = 0.0f, sr = 0.0f, sv = 0.0f, sa = 0.0f, dist = 0.0f;
-                    bool over = false;
-                    const bool in_mask = lane < NB && ((cfg.reset_body_mask >> lane) & 1u);
-                    if (lane < NB) {
-                        reward_terms_body_fma(body, ref, sp, sr, sv, sa);
-                        if (in_mask) {
-                            dist = norm3(body.p - ref.p);
-                            over = dist > __ldg(in.term_dist + j);
-                        }
-                        if (out.ref_state_t) store_ref(out.ref_state_t + e * FRAME_F, j, ref);
-                        float* o = my_tile;
-                        if (j == 0) o[0] = root_p.z;                                      // common.py:40
-                        self_obs_pos_rot_fma(body, root_p, hz, hw, hrot, j, o + 1 + 3 * (j - 1), o + 70 + 6 * j);   // vel / ang blocks: role B
+            float hz = 0.0f, hw = 1.0f;
+            if (valid) heading_quat_direct(root_q, hz, hw);                    // upright start: no base-rot removal
+            const ZRot hrot = zrot_make(hz, hw);
+            if (role == 0) {
+                // ============ role A: reward, reset, power, self observation (reference at t) ============
+                float* rj = red + (slot * NB + j) * 8;
+                if (valid) {
+                    float sp, sr, sv, sa, dist = 0.0f;
+                    reward_terms_body_fma(body, ref, sp, sr, sv, sa);
+                    if ((cfg.reset_body_mask >> j) & 1u) {
+                        dist = norm3(body.p - ref.p);
+                        if (!cfg.use_mean) dist = (dist > __ldg(in.term_dist + j)) ? 1.0f : 0.0f;     // common.py:347-350 (any)
                     }
-                    sp = warp_sum(sp); sr = warp_sum(sr); sv = warp_sum(sv); sa = warp_sum(sa);
+                    *reinterpret_cast<float4*>(rj) = make_float4(sp, sr, sv, sa);
+                    *reinterpret_cast<float2*>(rj + 4) = make_float2(dist, power);
+                    if (out.ref_state_t) store_ref(out.ref_state_t + e * FRAME_F, j, ref);
+                    float* o = my_tile;
+                    if (j == 0) o[0] = root_p.z;                                          // common.py:40
+                    self_obs_pos_rot_fma(body, root_p, hz, hw, hrot, j, o + 1 + 3 * (j - 1), o + 70 + 6 * j);   // vel / ang blocks: role B
+                }
+                group_sync(bar_id);
+                {   // second stage: lane (value v, part p) of the env adds bodies 6p .. 6p+5, in order
+                    const int v = j >> 2, p4 = j & 3;
+                    const float* src = red + (slot * NB + 6 * p4) * 8 + v;
+                    float s = src[0];
+#pragma unroll
+                    for (int k = 1; k < 6; ++k) s = s + src[8 * k];
+                    red2[(slot * 6 + v) * 4 + p4] = s;
+                }
+                group_sync(bar_id);
+                if (valid && j == 0) {      // one leader lane per env: fixed-order totals and the env-level tail
+                    float tot[6];
+#pragma unroll
+                    for (int v = 0; v < 6; ++v) {
+                        const float4 q4 = *reinterpret_cast<const float4*>(red2 + (slot * 6 + v) * 4);
+                        tot[v] = ((q4.x + q4.y) + q4.z) + q4.w;
+                    }
                     bool fallen = false;
                     if (cfg.enable_early_termination) {
-                        if (cfg.use_mean) {
-                            const float total = warp_sum(in_mask ? dist : 0.0f);
+                        if (cfg.use_mean) {                                               // common.py:342-346
                             const int first = __ffs(cfg.reset_body_mask) - 1;
-                            fallen = (total / (float)__popc(cfg.reset_body_mask & 0xffffffu)) > __ldg(in.term_dist + first);
+                            fallen = (tot[4] / (float)__popc(cfg.reset_body_mask & 0xffffffu)) > __ldg(in.term_dist + first);
                         } else {
-                            fallen = __any_sync(FULL, over);
+                            fallen = tot[4] > 0.0f;
                         }
                         fallen = fallen && (cur.prog > 1);                                // common.py:354
                     }
-                    if (in.dof_force) power = warp_sum(power);
-                    if (lane == 0) {
-                        float raw[4];
-                        float rew = reward_from_sq_sums(sp, sr, sv, sa, (float)NB, cfg.k, cfg.w, raw);
-                        float* rr = out.reward_raw + e * out.raw_stride;
-                        rr[0] = raw[0]; rr[1] = raw[1]; rr[2] = raw[2]; rr[3] = raw[3];
-                        if (in.dof_force) {
-                            float pr = -cfg.power_coef * power;
-                            if (cur.prog <= 3) pr = 0.0f;
-                            rew = rew + pr;
-                            rr[4] = pr;
-                        }
-                        out.reward[e] = rew;
-                        out.terminated[e] = fallen ? 1 : 0;
-                        out.reset[e] = (cur.t >= cur.mlen) ? 1 : (fallen ? 1 : 0);        // humanoid_phc.py:1315, common.py:362
+                    float raw[4];
+                    float rew = reward_from_sq_sums(tot[0], tot[1], tot[2], tot[3], (float)NB, cfg.k, cfg.w, raw);
+                    float* rr = out.reward_raw + e * out.raw_stride;
+                    rr[0] = raw[0]; rr[1] = raw[1]; rr[2] = raw[2]; rr[3] = raw[3];
+                    if (in.dof_force) {
+                        float pr = -cfg.power_coef * tot[5];
+                        if (cur.prog <= 3) pr = 0.0f;
+                        rew = rew + pr;
+                        rr[4] = pr;
                     }
-                } else if (lane < NB) {
-                    // ============ role B: imitation observation (reference at t+1) ============================
-                    if (out.ref_state_t1) store_ref(out.ref_state_t1 + e * FRAME_F, j, ref);
-                    self_obs_vel_ang_fma(body, hrot, my_tile + 214 + 3 * j, my_tile + 286 + 3 * j);      // balances the two roles
-                    float* q = my_tile + OBS_SELF;
-                    task_obs_body_fma(body, ref, root_p, hz, hw, hrot, q + 3 * j, q + 72 + 6 * j, q + 216 + 3 * j, q + 288 + 3 * j,
-                                  q + 360 + 3 * j, q + 432 + 6 * j);
+                    out.reward[e] = rew;
+                    out.terminated[e] = fallen ? 1 : 0;
+                    out.reset[e] = (cur.t >= cur.mlen) ? 1 : (fallen ? 1 : 0);            // humanoid_phc.py:1315, common.py:362
                 }
+            } else if (valid) {
+                // ============ role B: imitation observation (reference at t+1) + self vel / ang-vel ===========
+                if (out.ref_state_t1) store_ref(out.ref_state_t1 + e * FRAME_F, j, ref);
+                self_obs_vel_ang_fma(body, hrot, my_tile + 214 + 3 * j, my_tile + 286 + 3 * j);
+                float* q = my_tile + OBS_SELF;
+                task_obs_body_fma(body, ref, root_p, hz, hw, hrot, q + 3 * j, q + 72 + 6 * j, q + 216 + 3 * j, q + 288 + 3 * j,
+                                  q + 360 + 3 * j, q + 432 + 6 * j);
             }
             fence_proxy_async();            // tile rows were written by ordinary stores; the writers read them through TMA
             __syncwarp();
@@ -440,16 +464,18 @@ __global__ void __maxnreg__(ST_MAXREG) step_fused_kernel(const StepArgs a) {   /
                 mbar_wait<ST_WHINT>(&full[q % ST_TILES], (q / ST_TILES) & 1);
             }
             const int d = p % ST_PLANS;
-            if (lane < ST_CWARPS) plans[d * ST_CWARPS + lane] = make_plan(a, blk * ST_ENVS + lane % ST_ENVS, lane / ST_ENVS);
+            if (lane < ST_NBUF) plans[d * ST_NBUF + lane] = make_plan(a, blk * ST_ENVS + lane % ST_ENVS, lane / ST_ENVS);
             __syncwarp();
             if (lane == 0) mbar_arrive(&pfull[d]);
         }
     }
 }
 
-constexpr size_t ST_SMEM = (size_t)(ST_TILES * ST_ENVS * OBS_W + ST_CWARPS * ST_WBUF_F) * sizeof(float) + ST_PLANS * ST_CWARPS * sizeof(EnvPlan) +
+constexpr size_t ST_SMEM = (size_t)(ST_TILES * ST_ENVS * OBS_W + ST_NBUF * ST_WBUF_F + ST_ENVS * NB * 8 + ST_ENVS * 24) * sizeof(float) +
+                           ST_PLANS * ST_NBUF * sizeof(EnvPlan) +
                            (2 * ST_TILES + ST_PLANS) * sizeof(uint64_t);
-static_assert(sizeof(EnvPlan) == 48 && ST_CWARPS <= 32, "plan record layout");
+static_assert(sizeof(EnvPlan) == 48, "plan record layout");
+static_assert(ST_SMEM <= 227 * 1024, "shared memory budget");
 
 }  // namespace phc
 
