@@ -91,6 +91,18 @@ def measured_peak_gbs():
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
+def ncu_traffic(n_envs):
+    """DRAM bytes per launch of the dominant kernel from the committed ncu capture (only valid at the captured size)."""
+    p = os.path.join(ROOT, "profiles", "r1_step_fused_traffic.json")
+    try:
+        t = json.load(open(p))
+        if int(t["envs"]) == int(n_envs):
+            return int(t["dram_bytes_read"]) + int(t["dram_bytes_write"])
+    except Exception:
+        pass
+    return None
+
+
 def cpu_port_rate(n_envs, iters, warmup, threads, tables_host, seed=1):
     """env-steps/s of the reference torch-CPU path (full step + RunningNorm.forward + the amortised c_gae share)."""
     import numpy as np
@@ -302,7 +314,8 @@ def main():
             "ms_per_step": elapsed_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic", "config": workload_config(N, world),
             "roofline": {"bound": "hbm", "kernel": "phc::step_fused_kernel<true>", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                         "frac": achieved / peak, "traffic": ncu_traffic(N), "peak_source": peak_src,
+                         "algorithmic_bytes_per_launch": STEP_BYTES * N,
                          "algorithmic_bytes_per_env_step": STEP_BYTES, "kernel_ms": kern_ms,
                          "whole_step_gbs": (STEP_BYTES + GAE_BYTES_PER_ELEM) * N * K / (elapsed_ms * 1e-3) / 1e9},
             "gpu_launches": launches["n"], "clocks": clocks,
