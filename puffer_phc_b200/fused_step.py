@@ -165,3 +165,26 @@ class FusedStep:
             v.copy_(out[k], non_blocking=True)
         torch.cuda.current_stream(self.device).synchronize()
         return self._host_out
+
+    # ---- CUDA-graph replay: at small batch sizes the step is launch-bound (4096 envs = a few microseconds of GPU work) ------
+    def capture(self, body_state, progress_buf, motion_start_times, motion_start_times_offset, sampled_motion_ids, global_offset,
+                dof_force=None, dof_vel=None, out: Optional[Dict[str, torch.Tensor]] = None, extra=None):
+        """Capture one step (plus an optional ``extra()`` callable that enqueues further kernels, e.g. the GAE pass) on the
+        given, fixed input/output buffers into a CUDA graph.  Returns ``(graph, outputs)``; call ``graph.replay()`` each
+        step after the simulator has refreshed the input buffers in place (as Isaac Gym does)."""
+        args = (body_state, progress_buf, motion_start_times, motion_start_times_offset, sampled_motion_ids, global_offset, dof_force, dof_vel)
+        side = torch.cuda.Stream(device=self.device)
+        side.wait_stream(torch.cuda.current_stream(self.device))
+        with torch.cuda.stream(side):
+            for _ in range(2):                      # warm-up outside capture (lazy initialisation, allocator)
+                res = self(*args, out=out)
+                if extra is not None:
+                    extra()
+        torch.cuda.current_stream(self.device).wait_stream(side)
+        torch.cuda.synchronize(self.device)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            res = self(*args, out=out)
+            if extra is not None:
+                extra()
+        return graph, res

@@ -375,3 +375,28 @@ def test_config4_amass_65536_envs(amass_lib):
     assert_equal(npy(got["blend"]).view(np.uint32), bl.view(np.uint32), "blend bits")
     for k in want:
         assert_close(npy(got[k]), want[k], what=f"65536 {k}")
+
+
+def test_fused_step_cuda_graph_replay(golden):
+    """The step captured in a CUDA graph (small batches are launch-bound) reproduces the eager outputs bit for bit and
+    follows in-place updates of the input buffers."""
+    from puffer_phc_b200.fused_step import FusedStep, StepConfig
+    S = golden["synth_step"]
+    lib = make_lib(golden["synth_tables"])
+    _, eager = _fused(lib, S)
+    eager = {k: v.clone() for k, v in eager.items()}
+    N = S["in_progress"].shape[0]
+    fs = FusedStep(lib, N, StepConfig())
+    bufs = [cu(S[k]) for k in ("in_body_state", "in_progress", "in_start_time", "in_start_offset", "in_motion_ids", "in_global_offset",
+                               "in_dof_force", "in_dof_vel")]
+    graph, out = fs.capture(*bufs)
+    out["obs"].zero_()
+    graph.replay()
+    torch.cuda.synchronize()
+    for k in ("obs", "reward", "reward_raw", "reset", "terminated"):
+        assert torch.equal(out[k], eager[k]), k
+    bufs[1].add_(1)                       # progress_buf += 1, in place, as the env does before the next step
+    graph.replay()
+    want = fs(*bufs, out={k: torch.empty_like(v) for k, v in eager.items()})
+    torch.cuda.synchronize()
+    assert torch.equal(out["obs"], want["obs"]) and not torch.equal(out["obs"], eager["obs"])
