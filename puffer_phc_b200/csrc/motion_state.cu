@@ -2,8 +2,10 @@
 // (reference puffer_phc/motion_lib.py:526-535, 549-665) and the packed-frame table builder.
 //
 // One warp per query, lane j = body j: frame-index/blend (bit-exact op order), the row gathers of the
-// two bracketing frames, lerp of pos/vel/ang-vel/dof-vel, slerp of global and local rotations and
-// the quaternion -> exp-map of the local rotations, all in one pass; nothing is materialised.
+// two bracketing frames, lerp of pos/vel/ang-vel/dof-vel (bit-exact: pure mul/add), slerp of global and local
+// rotations and the quaternion -> exp-map of the local rotations, all in one pass; nothing is materialised.
+// The rotations use the cheaper, algebraically identical forms of phc_math.cuh (same branch decisions, a few ulp
+// from the reference's op sequence): the kernel is instruction-bound with the libm sin/cos/atan2 chain.
 #include "phc_common.cuh"
 
 namespace phc {
@@ -66,14 +68,14 @@ __global__ void __launch_bounds__(MS_WARPS * 32) motion_state_kernel(const State
             if (o.root_ang_vel && j == 0) st3(o.root_ang_vel + q * 3, p);
         }
         if (o.rb_rot || o.root_rot) {
-            Q4 r = slerp(ldg4a(T.grs + (f0 * NB + j) * 4), ldg4a(T.grs + (f1 * NB + j) * 4), blend);
+            Q4 r = slerp_rcp(ldg4a(T.grs + (f0 * NB + j) * 4), ldg4a(T.grs + (f1 * NB + j) * 4), blend);
             if (o.rb_rot) *reinterpret_cast<float4*>(o.rb_rot + (q * NB + j) * 4) = make_float4(r.x, r.y, r.z, r.w);
             if (o.root_rot && j == 0) st4(o.root_rot + q * 4, r);
         }
         if (j >= 1) {
             if (o.dof_pos) {   // motion_lib.py:605-606, 670-673
-                Q4 r = slerp(ldg4a(T.lrs + (f0 * NB + j) * 4), ldg4a(T.lrs + (f1 * NB + j) * 4), blend);
-                st3(o.dof_pos + q * NDOF + (j - 1) * 3, quat_exp_map(r));
+                Q4 r = slerp_rcp(ldg4a(T.lrs + (f0 * NB + j) * 4), ldg4a(T.lrs + (f1 * NB + j) * 4), blend);
+                st3(o.dof_pos + q * NDOF + (j - 1) * 3, quat_exp_map_fast(r));
             }
             if (o.dof_vel) {
                 V3 p0 = ldg3(T.dvs + (f0 * 23 + (j - 1)) * 3), p1 = ldg3(T.dvs + (f1 * 23 + (j - 1)) * 3);

@@ -225,6 +225,18 @@ PHC_HD V3 quat_exp_map(Q4 q) {
     return V3{a * (q.x / s), a * (q.y / s), a * (q.z / s)};
 }
 
+// quat_to_exp_map with the angle wrapped in closed form: normalize_angle(2 acos w) is 2 acos w - 2 pi when it exceeds pi
+// (the reference's atan2(sin a, cos a) round trip gives the same value to a few ulp; they only differ in sign for an exact
+// 180-degree rotation, w == 0, a measure-zero knife edge).
+PHC_HD V3 quat_exp_map_fast(Q4 q) {
+    float s = sqrtf(1.0f - q.w * q.w);
+    if (!(fabsf(s) > 1e-5f)) return V3{0.0f, 0.0f, 0.0f};
+    float a = 2.0f * acosf(q.w);
+    if (a > 3.14159265358979323846f) a = a - 6.28318530717958647692f;
+    const float k = a / s;
+    return V3{k * q.x, k * q.y, k * q.z};
+}
+
 // slerp (torch_utils.py:110-131).  The two torch.where fall-backs are evaluated first (they
 // discard the trigonometric result anyway): q0 when |cos| >= 1, the un-normalised midpoint when
 // |sin| < 1e-3.  No renormalisation.

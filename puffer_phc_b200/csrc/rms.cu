@@ -3,7 +3,7 @@
 //   update   (:23-34)  split into   moments (per-column sum / sum of squares, fp64, deterministic)
 //                                   [all-reduce across ranks happens here, on the moments buffer]
 //                                   finalize (batch mean / biased var -> running average, count += 1)
-// Memory-bound column pass: thread = column (coalesced rows), 4 independent rows in flight per thread.
+// Memory-bound column pass: thread = column (coalesced rows), 8 independent rows in flight per thread.
 #include "phc_common.cuh"
 
 namespace phc {
@@ -24,16 +24,29 @@ __global__ void __launch_bounds__(RMS_THREADS) rms_forward_vec_kernel(const floa
     float* s_den = sm + C;
     for (int c = threadIdx.x; c < C; c += blockDim.x) { s_mean[c] = __ldg(mean + c); s_den[c] = sqrtf(__ldg(var + c) + eps); }
     __syncthreads();
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
-        float4 v = __ldg(x + i);
-        int c = (int)((i << 2) % C);
-        float r[4] = {v.x, v.y, v.z, v.w};
+    // four independent 16-byte loads in flight per thread before any arithmetic (the division chain is long)
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i0 < n4; i0 += 4 * stride) {
+        float4 v[4];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            r[u] = norm_clamp(r[u], s_mean[c], s_den[c], clip);
-            c = (c + 1 == C) ? 0 : c + 1;
+        for (int k = 0; k < 4; ++k) {
+            const int64_t i = i0 + k * stride;
+            if (i < n4) v[k] = __ldg(x + i);
         }
-        y[i] = make_float4(r[0], r[1], r[2], r[3]);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int64_t i = i0 + k * stride;
+            if (i < n4) {
+                int c = (int)((i << 2) % C);
+                float r[4] = {v[k].x, v[k].y, v[k].z, v[k].w};
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    r[u] = norm_clamp(r[u], s_mean[c], s_den[c], clip);
+                    c = (c + 1 == C) ? 0 : c + 1;
+                }
+                y[i] = make_float4(r[0], r[1], r[2], r[3]);
+            }
+        }
     }
 }
 
@@ -59,16 +72,71 @@ __global__ void __launch_bounds__(RMS_THREADS) rms_moments_kernel(const float* _
     const int64_t r1 = (r0 + rows_per_block < B) ? r0 + rows_per_block : B;
     double s = 0.0, q = 0.0;
     int64_t r = r0;
-    for (; r + 4 <= r1; r += 4) {
-        const float a0 = __ldg(x + (r + 0) * xs + c), a1 = __ldg(x + (r + 1) * xs + c);
-        const float a2 = __ldg(x + (r + 2) * xs + c), a3 = __ldg(x + (r + 3) * xs + c);
-        const double d0 = a0, d1 = a1, d2 = a2, d3 = a3;
-        s += d0; q += d0 * d0; s += d1; q += d1 * d1; s += d2; q += d2 * d2; s += d3; q += d3 * d3;
+    for (; r + 8 <= r1; r += 8) {          // eight independent rows in flight per thread
+        float a[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) a[k] = __ldg(x + (r + k) * xs + c);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) { const double d = a[k]; s += d; q = fma(d, d, q); }
     }
-    for (; r < r1; ++r) { const double d = __ldg(x + r * xs + c); s += d; q += d * d; }
+    for (; r < r1; ++r) { const double d = __ldg(x + r * xs + c); s += d; q = fma(d, d, q); }
     double* p = partial + (int64_t)blockIdx.x * 2 * C;
     p[c] = s;
     p[C + c] = q;
+}
+
+// Streaming variant for even C <= 2048 with 8-byte aligned rows: a block owns a contiguous range of rows and sweeps them
+// front to back (purely sequential DRAM traffic), thread = up to 4 column pairs (float2 loads), two rows in flight.
+constexpr int RMS_MAXPAIRS = 4;
+__global__ void __launch_bounds__(RMS_THREADS) rms_moments_rows_kernel(const float* __restrict__ x, int64_t xs, int64_t B, int C,
+                                                                       int64_t rows_per_block, double* __restrict__ partial) {
+    const int64_t r0 = (int64_t)blockIdx.x * rows_per_block;
+    const int64_t r1 = (r0 + rows_per_block < B) ? r0 + rows_per_block : B;
+    const int npairs = C >> 1;
+    double s[RMS_MAXPAIRS][2], q[RMS_MAXPAIRS][2];
+#pragma unroll
+    for (int u = 0; u < RMS_MAXPAIRS; ++u) { s[u][0] = s[u][1] = q[u][0] = q[u][1] = 0.0; }
+    int64_t r = r0;
+    for (; r + 2 <= r1; r += 2) {
+        float2 a[RMS_MAXPAIRS], b[RMS_MAXPAIRS];
+#pragma unroll
+        for (int u = 0; u < RMS_MAXPAIRS; ++u) {
+            const int cp = threadIdx.x + u * RMS_THREADS;
+            if (cp < npairs) {
+                a[u] = __ldg(reinterpret_cast<const float2*>(x + r * xs) + cp);
+                b[u] = __ldg(reinterpret_cast<const float2*>(x + (r + 1) * xs) + cp);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < RMS_MAXPAIRS; ++u) {
+            const int cp = threadIdx.x + u * RMS_THREADS;
+            if (cp < npairs) {
+                double d;
+                d = a[u].x; s[u][0] += d; q[u][0] = fma(d, d, q[u][0]);
+                d = a[u].y; s[u][1] += d; q[u][1] = fma(d, d, q[u][1]);
+                d = b[u].x; s[u][0] += d; q[u][0] = fma(d, d, q[u][0]);
+                d = b[u].y; s[u][1] += d; q[u][1] = fma(d, d, q[u][1]);
+            }
+        }
+    }
+    for (; r < r1; ++r) {
+#pragma unroll
+        for (int u = 0; u < RMS_MAXPAIRS; ++u) {
+            const int cp = threadIdx.x + u * RMS_THREADS;
+            if (cp < npairs) {
+                const float2 a = __ldg(reinterpret_cast<const float2*>(x + r * xs) + cp);
+                double d;
+                d = a.x; s[u][0] += d; q[u][0] = fma(d, d, q[u][0]);
+                d = a.y; s[u][1] += d; q[u][1] = fma(d, d, q[u][1]);
+            }
+        }
+    }
+    double* p = partial + (int64_t)blockIdx.x * 2 * C;
+#pragma unroll
+    for (int u = 0; u < RMS_MAXPAIRS; ++u) {
+        const int cp = threadIdx.x + u * RMS_THREADS;
+        if (cp < npairs) { p[2 * cp] = s[u][0]; p[2 * cp + 1] = s[u][1]; p[C + 2 * cp] = q[u][0]; p[C + 2 * cp + 1] = q[u][1]; }
+    }
 }
 
 // moments[1 + i] += sum_p partial[p][i] for i in [0, 2C); moments[0] += rows.  Deterministic: a block owns 32
@@ -166,8 +234,12 @@ extern "C" int phc_rms_moments(const float* x, int64_t x_stride, int64_t B, int 
     if (row_blocks > moments_row_blocks()) row_blocks = moments_row_blocks();
     const int64_t rows_per_block = (B + row_blocks - 1) / row_blocks;
     row_blocks = (B + rows_per_block - 1) / rows_per_block;
-    dim3 grid((unsigned)row_blocks, (unsigned)((C + RMS_THREADS - 1) / RMS_THREADS));
-    rms_moments_kernel<<<grid, RMS_THREADS, 0, s>>>(x, x_stride, B, C, rows_per_block, scratch);
+    if ((C & 1) == 0 && C <= 2 * RMS_MAXPAIRS * RMS_THREADS && (x_stride & 1) == 0 && aligned8(x)) {
+        rms_moments_rows_kernel<<<(unsigned)row_blocks, RMS_THREADS, 0, s>>>(x, x_stride, B, C, rows_per_block, scratch);
+    } else {
+        dim3 grid((unsigned)row_blocks, (unsigned)((C + RMS_THREADS - 1) / RMS_THREADS));
+        rms_moments_kernel<<<grid, RMS_THREADS, 0, s>>>(x, x_stride, B, C, rows_per_block, scratch);
+    }
     int rc = check_launch(fn);
     if (rc) return rc;
     rms_reduce_kernel<<<(2 * C + 31) / 32, 256, 0, s>>>(scratch, (int)row_blocks, B, C, moments);

@@ -113,13 +113,13 @@ extern "C" int harness_dof_pos(const phc_motion_tables* T, const int64_t* ids, c
         for (int j = 0; j < NB; ++j) {
             const float* a = T->grs + (f0 * NB + j) * 4;
             const float* b = T->grs + (f1 * NB + j) * 4;
-            Q4 r = slerp(Q4{a[0], a[1], a[2], a[3]}, Q4{b[0], b[1], b[2], b[3]}, bl);
+            Q4 r = slerp_rcp(Q4{a[0], a[1], a[2], a[3]}, Q4{b[0], b[1], b[2], b[3]}, bl);
             float* o = rb_rot + (q * NB + j) * 4;
             o[0] = r.x; o[1] = r.y; o[2] = r.z; o[3] = r.w;
             if (j >= 1) {
                 a = T->lrs + (f0 * NB + j) * 4;
                 b = T->lrs + (f1 * NB + j) * 4;
-                V3 e = quat_exp_map(slerp(Q4{a[0], a[1], a[2], a[3]}, Q4{b[0], b[1], b[2], b[3]}, bl));
+                V3 e = quat_exp_map_fast(slerp_rcp(Q4{a[0], a[1], a[2], a[3]}, Q4{b[0], b[1], b[2], b[3]}, bl));
                 put3(dof_pos + q * NDOF + (j - 1) * 3, e);
             }
         }

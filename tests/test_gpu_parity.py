@@ -400,3 +400,17 @@ def test_fused_step_cuda_graph_replay(golden):
     want = fs(*bufs, out={k: torch.empty_like(v) for k, v in eager.items()})
     torch.cuda.synchronize()
     assert torch.equal(out["obs"], want["obs"]) and not torch.equal(out["obs"], eager["obs"])
+
+
+def test_running_norm_update_layouts():
+    """Both moment kernels (streaming rows for even C, column chunks otherwise / for odd strides) against fp64 numpy."""
+    from puffer_phc_b200.policies.running_norm import RunningNorm
+    g = torch.Generator().manual_seed(0)
+    for B, C, pitch in ((1000, 934, 934), (777, 935, 935), (513, 934, 937), (3, 6, 6), (70000, 934, 934)):
+        x = (torch.randn(B, pitch, generator=g) * 3 + 1.5).to(DEV)[:, :C]
+        rn = RunningNorm(C).to(DEV)
+        rn.update(x)
+        x64 = x.double().cpu().numpy()
+        np.testing.assert_allclose(npy(rn.running_mean)[0], x64.mean(0), rtol=1e-6, atol=1e-7)
+        np.testing.assert_allclose(npy(rn.running_var)[0], x64.var(0), rtol=1e-5, atol=1e-9)
+        assert float(rn.count) == 2.0
