@@ -265,6 +265,8 @@ PHC_HD Q4 slerp_rcp(Q4 q0, Q4 q1, float t) {
     float s = sqrtf(1.0f - c * c);
     if (fabsf(s) < 0.001f)
         return Q4{0.5f * q0.x + 0.5f * q1.x, 0.5f * q0.y + 0.5f * q1.y, 0.5f * q0.z + 0.5f * q1.z, 0.5f * q0.w + 0.5f * q1.w};
+    // NOTE: no shortcut for t == 0 or 1.  The reference's ratio sin(h)/sqrt(1-c*c) is NOT 1 there: 1-c*c cancels, so the
+    // ratio is off by up to ~1.5e-4 for nearby frames, and parity means reproducing that value (same c, same 1-c*c).
     float h = acosf(c);
     float inv = 1.0f / s;
     float ra = sin_0_halfpi((1.0f - t) * h) * inv;
