@@ -183,7 +183,7 @@ def workload_config(envs, world, sample_note=None):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=2000)
+    ap.add_argument("--steps", type=int, default=5000)
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--envs", type=int, default=65536, help="envs per GPU")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
