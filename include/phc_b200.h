@@ -114,6 +114,19 @@ int phc_motion_state(const phc_motion_tables *t, const int64_t *motion_ids, cons
                      const float *offset /* [B,3] or NULL */, int64_t B, const phc_motion_state_out *out,
                      phc_stream_t stream);
 
+/* Reset path ("next" row f1): HumanoidPHC._sample_ref_state + _set_env_state for the envs listed in env_ids
+ * (puffer_phc/envs/humanoid_phc.py:843-873, 899-929): one get_motion_state query per reset env
+ * (motion id = sampled_motion_ids[e], time = motion_times[i], offset = global_offset[e]) whose result is written
+ * straight into the env's state tensors at row e instead of being materialised and scattered by 12 index_put ops:
+ *   root_states[e]      = root_pos | root_rot | root_vel | root_ang_vel           [N,13]
+ *   dof_pos[e], dof_vel[e]                                                          [N,69]
+ *   body_state[e, j]    = rg_pos | rb_rot | body_vel | body_ang_vel, j < 24         AoS [N, env_stride]
+ * env_ids: [K] int64, ascending and unique (torch.nonzero order); motion_times: [K]. Any output may be NULL. */
+int phc_reset_ref_state(const phc_motion_tables *t, const int64_t *env_ids, const int64_t *sampled_motion_ids /* [N] */,
+                        const float *motion_times /* [K] */, const float *global_offset /* [N,3] or NULL */, int64_t K,
+                        float *root_states, float *dof_pos, float *dof_vel, float *body_state, int64_t env_stride,
+                        phc_stream_t stream);
+
 /* MotionLibBase.sample_time_interval arithmetic (puffer_phc/motion_lib.py:526-535); the uniform
  * phase stays on the caller's torch generator.  out = float(int64((phase*len)/(1/30))) * (1/30).
  * div_mode 0: IEEE division (torch CPU); 1: multiply by fp32 reciprocal (torch CUDA divides a

@@ -17,7 +17,7 @@ _lib = None
 c_f32p, c_i64p, c_u8p, c_i16p, c_f64p = C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p
 
 EXPORTS = (
-    "phc_version", "phc_last_error", "phc_pack_frames", "phc_motion_state", "phc_sample_time_interval",
+    "phc_version", "phc_last_error", "phc_pack_frames", "phc_motion_state", "phc_reset_ref_state", "phc_sample_time_interval",
     "phc_imitation_obs_v6", "phc_self_obs_smpl_max", "phc_imitation_reward", "phc_im_reset",
     "phc_step_num_partials", "phc_step_fused", "phc_rms_forward", "phc_rms_scratch_doubles", "phc_rms_moments",
     "phc_rms_reduce_partials", "phc_rms_finalize", "phc_gae",
@@ -77,6 +77,7 @@ def _declare(lib):
     lib.phc_last_error.argtypes, lib.phc_last_error.restype = [], C.c_char_p
     lib.phc_pack_frames.argtypes = [C.POINTER(MotionTables), P, P]
     lib.phc_motion_state.argtypes = [C.POINTER(MotionTables), P, P, P, I64, C.POINTER(MotionStateOut), P]
+    lib.phc_reset_ref_state.argtypes = [C.POINTER(MotionTables), P, P, P, P, I64, P, P, P, P, I64, P]
     lib.phc_sample_time_interval.argtypes = [P, P, I64, I, P, P]
     lib.phc_imitation_obs_v6.argtypes = [View] * 10 + [I64, I, I, I, P, I64, P]
     lib.phc_self_obs_smpl_max.argtypes = [View] * 4 + [I64, I, I, I, I, P, I64, P]

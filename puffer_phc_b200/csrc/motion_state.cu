@@ -90,6 +90,61 @@ __global__ void __launch_bounds__(MS_WARPS * 32) motion_state_kernel(const State
     if (o.motion_limb_weights && lane < 10) o.motion_limb_weights[q * 10 + lane] = __ldg(T.limb_weights + id * 10 + lane);
 }
 
+// Reset path: the same query, written straight into the env's state tensors (humanoid_phc.py:843-873, 899-929).
+struct ResetArgs2 {
+    phc_motion_tables t;
+    const int64_t* env_ids; const int64_t* motion_ids; const float* times; const float* offset; int64_t K;
+    float* root_states; float* dof_pos; float* dof_vel; float* body_state; int64_t env_stride;
+};
+
+__global__ void __launch_bounds__(MS_WARPS * 32) reset_ref_state_kernel(const ResetArgs2 a) {
+    const int lane = threadIdx.x & 31;
+    const int64_t i = (int64_t)blockIdx.x * MS_WARPS + (threadIdx.x >> 5);
+    if (i >= a.K) return;
+    const phc_motion_tables& T = a.t;
+    const int64_t e = __ldg(a.env_ids + i);
+    const int64_t id = __ldg(a.motion_ids + e);
+    int64_t i0, i1;
+    float blend;
+    frame_blend(__ldg(a.times + i), __ldg(T.motion_len + id), __ldg(T.num_frames + id), __ldg(T.motion_dt + id), i0, i1, blend);
+    const int64_t ls = __ldg(T.length_starts + id);
+    const int64_t f0 = i0 + ls, f1 = i1 + ls;
+    const float one_m = 1.0f - blend;
+    if (lane >= NB) return;
+    const int j = lane;
+    V3 off{0.0f, 0.0f, 0.0f};
+    if (a.offset) off = ldg3(a.offset + e * 3);
+    const bool need_body = a.body_state || (a.root_states && j == 0);
+    if (need_body) {
+        V3 p0 = ldg3(T.gts + (f0 * NB + j) * 3), p1 = ldg3(T.gts + (f1 * NB + j) * 3);
+        V3 p{lerp(p0.x, p1.x, one_m, blend), lerp(p0.y, p1.y, one_m, blend), lerp(p0.z, p1.z, one_m, blend)};
+        if (a.offset) { p.x = p.x + off.x; p.y = p.y + off.y; p.z = p.z + off.z; }
+        const Q4 r = slerp_rcp(ldg4a(T.grs + (f0 * NB + j) * 4), ldg4a(T.grs + (f1 * NB + j) * 4), blend);
+        V3 v0 = ldg3(T.gvs + (f0 * NB + j) * 3), v1 = ldg3(T.gvs + (f1 * NB + j) * 3);
+        const V3 v{lerp(v0.x, v1.x, one_m, blend), lerp(v0.y, v1.y, one_m, blend), lerp(v0.z, v1.z, one_m, blend)};
+        V3 w0 = ldg3(T.gavs + (f0 * NB + j) * 3), w1 = ldg3(T.gavs + (f1 * NB + j) * 3);
+        const V3 w{lerp(w0.x, w1.x, one_m, blend), lerp(w0.y, w1.y, one_m, blend), lerp(w0.z, w1.z, one_m, blend)};
+        if (a.body_state) {
+            float* b = a.body_state + e * a.env_stride + REC * j;
+            st3(b, p); st4(b + 3, r); st3(b + 7, v); st3(b + 10, w);
+        }
+        if (a.root_states && j == 0) {
+            float* b = a.root_states + e * REC;
+            st3(b, p); st4(b + 3, r); st3(b + 7, v); st3(b + 10, w);
+        }
+    }
+    if (j >= 1) {
+        if (a.dof_pos) {
+            const Q4 r = slerp_rcp(ldg4a(T.lrs + (f0 * NB + j) * 4), ldg4a(T.lrs + (f1 * NB + j) * 4), blend);
+            st3(a.dof_pos + e * NDOF + (j - 1) * 3, quat_exp_map_fast(r));
+        }
+        if (a.dof_vel) {
+            V3 p0 = ldg3(T.dvs + (f0 * 23 + (j - 1)) * 3), p1 = ldg3(T.dvs + (f1 * 23 + (j - 1)) * 3);
+            st3(a.dof_vel + e * NDOF + (j - 1) * 3, V3{lerp(p0.x, p1.x, one_m, blend), lerp(p0.y, p1.y, one_m, blend), lerp(p0.z, p1.z, one_m, blend)});
+        }
+    }
+}
+
 __global__ void sample_time_interval_kernel(const float* __restrict__ phase, const float* __restrict__ len, int64_t n,
                                             int div_mode, float* __restrict__ out) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -143,6 +198,25 @@ extern "C" int phc_motion_state(const phc_motion_tables* t, const int64_t* motio
     const int64_t blocks = (B + MS_WARPS - 1) / MS_WARPS;
     motion_state_kernel<<<(unsigned)blocks, MS_WARPS * 32, 0, (cudaStream_t)stream>>>(a);
     return check_launch("phc_motion_state");
+}
+
+extern "C" int phc_reset_ref_state(const phc_motion_tables* t, const int64_t* env_ids, const int64_t* sampled_motion_ids,
+                                   const float* motion_times, const float* global_offset, int64_t K, float* root_states,
+                                   float* dof_pos, float* dof_vel, float* body_state, int64_t env_stride, phc_stream_t stream) {
+    const char* fn = "phc_reset_ref_state";
+    PHC_REQUIRE(t, PHC_EINVAL, "%s: tables is NULL", fn);
+    PHC_REQUIRE(K >= 0, PHC_EINVAL, "%s: K < 0", fn);
+    if (K == 0) return PHC_OK;
+    PHC_REQUIRE(env_ids && sampled_motion_ids && motion_times, PHC_EINVAL, "%s: env_ids / sampled_motion_ids / motion_times is NULL", fn);
+    PHC_REQUIRE(t->motion_len && t->motion_dt && t->num_frames && t->length_starts, PHC_EINVAL, "%s: per-motion tables missing", fn);
+    PHC_REQUIRE(!(body_state || root_states) || (t->gts && t->grs && t->gvs && t->gavs), PHC_EINVAL, "%s: gts/grs/gvs/gavs tables missing", fn);
+    PHC_REQUIRE(!dof_pos || t->lrs, PHC_EINVAL, "%s: lrs table missing", fn);
+    PHC_REQUIRE(!dof_vel || t->dvs, PHC_EINVAL, "%s: dvs table missing", fn);
+    PHC_REQUIRE(!body_state || env_stride >= NB * REC, PHC_ESHAPE, "%s: env_stride=%lld < 312", fn, (long long)env_stride);
+    PHC_REQUIRE(aligned16(t->grs) && aligned16(t->lrs), PHC_EALIGN, "%s: grs/lrs tables must be 16-byte aligned", fn);
+    ResetArgs2 a{*t, env_ids, sampled_motion_ids, motion_times, global_offset, K, root_states, dof_pos, dof_vel, body_state, env_stride};
+    reset_ref_state_kernel<<<(unsigned)((K + MS_WARPS - 1) / MS_WARPS), MS_WARPS * 32, 0, (cudaStream_t)stream>>>(a);
+    return check_launch(fn);
 }
 
 extern "C" int phc_sample_time_interval(const float* phase, const float* motion_len, int64_t n, int div_mode, float* out,
