@@ -26,6 +26,8 @@
 //     execute (32x redundantly) or wait on that dependent load chain.
 //   * Register budget: each SM sub-partition holds 16384 registers = 5 warps x 96 or 6 warps x 80 (default S = 8: 12 compute + 4 writer
 //     + 1 planner warps).  The flag-critical chain keeps the reference's fp32 op order.
+#include <type_traits>
+
 #include "phc_body.cuh"
 
 namespace phc {
@@ -65,7 +67,7 @@ constexpr int ST_PLANS = 4;                          // plan ring: plans are pro
 constexpr int ST_WPAIRS = (OBS_W / 2 + ST_WTHREADS - 1) / ST_WTHREADS;  // column pairs owned by a writer thread
 constexpr int ST_DOF_F = 144;                        // dof_force (69, padded to 72) | dof_vel (69, padded to 72)
 constexpr int ST_WBUF_F = 3 * FRAME_F + ST_DOF_F;    // per compute warp: sim record | frame 0 | frame 1 | dof force/vel
-constexpr unsigned SPIN_LIMIT = 1u << 28;            // a stuck mbarrier traps instead of hanging the GPU
+constexpr unsigned SPIN_LIMIT = 1u << 22;            // a stuck mbarrier traps (after a few seconds) instead of hanging the GPU
 
 struct StepArgs {
     phc_motion_tables t;
@@ -397,18 +399,21 @@ __global__ void __maxnreg__(ST_MAXREG) step_fused_kernel(const StepArgs a) {   /
                 c_inv[u] = make_float2(1.0f / sqrtf(__ldg(in.rms_var + c) + cfg.rms_eps), 1.0f / sqrtf(__ldg(in.rms_var + c + 1) + cfg.rms_eps));
             }
         }
-        auto column_pass = [&](const float* tile, int64_t e0, int r) {
+        // VEC = contiguous, aligned output rows (the normal case): one float2 store per pair, no pitched-row code in the loop
+        // (predicated-off stores would still occupy load/store issue slots).
+        auto column_pass = [&](const float* tile, int64_t e0, int r, auto vec) {
+            constexpr bool VEC = decltype(vec)::value;
 #pragma unroll
             for (int u = 0; u < ST_WPAIRS; ++u) {
                 const int c = 2 * (wtid + u * ST_WTHREADS);
                 if (c < OBS_W) {
                     const float2 x = *reinterpret_cast<const float2*>(tile + r * OBS_W + c);
-                    if (!a.obs_vec) { float* o = out.obs + (e0 + r) * out.obs_stride + c; o[0] = x.x; o[1] = x.y; }
+                    if (!VEC) { float* o = out.obs + (e0 + r) * out.obs_stride + c; o[0] = x.x; o[1] = x.y; }
                     if (do_norm) {   // (x - mean) / sqrt(var + eps) as a multiplication by the column's reciprocal (<= 1.5 ulp)
                         const float y0 = clamp_nan((x.x - c_mean[u].x) * c_inv[u].x, cfg.rms_clip);
                         const float y1 = clamp_nan((x.y - c_mean[u].y) * c_inv[u].y, cfg.rms_clip);
                         float* o = out.obs_norm + (e0 + r) * out.obs_stride + c;
-                        if (a.obs_vec) *reinterpret_cast<float2*>(o) = make_float2(y0, y1);
+                        if (VEC) *reinterpret_cast<float2*>(o) = make_float2(y0, y1);
                         else { o[0] = y0; o[1] = y1; }
                     }
                     if (do_mom) {    // xd*xd is exact in fp64, so fma(xd, xd, q) equals q + xd*xd
@@ -436,8 +441,13 @@ __global__ void __maxnreg__(ST_MAXREG) step_fused_kernel(const StepArgs a) {   /
             // ---- normalised copy + fp64 column moments from the same tile ----------------------------------------
             if (!a.obs_vec || do_norm || do_mom) {
                 // rolled on purpose: three warp roles share the instruction cache, and the pairs give the ILP
+                if (a.obs_vec) {
 #pragma unroll 1
-                for (int r = 0; r < rows; ++r) column_pass(tile, e0, r);
+                    for (int r = 0; r < rows; ++r) column_pass(tile, e0, r, std::true_type{});
+                } else {
+#pragma unroll 1
+                    for (int r = 0; r < rows; ++r) column_pass(tile, e0, r, std::false_type{});
+                }
             }
             if (bulk && wtid == 0) bulk_wait_read();     // the TMA engine has finished reading the tile from shared memory
             writers_sync();
