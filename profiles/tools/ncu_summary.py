@@ -4,7 +4,7 @@ per CUDA source line (SASS offsets from ncu --page source joined with nvdisasm -
     python profiles/tools/ncu_summary.py gpurun_out/<report>.ncu-rep [kernel-mangled-substring]
 """
 import csv, collections, re, sys, subprocess, glob
-rep=sys.argv[1]; kern=sys.argv[2] if len(sys.argv)>2 else 'step_fused_kernelILb1'
+rep=sys.argv[1]; kern=sys.argv[2] if len(sys.argv)>2 else 'step_fused_kernelILb1ELb0'
 subprocess.run(f'ncu -i {rep} --page raw --csv > /tmp/raw.csv 2>/dev/null', shell=True)
 subprocess.run(f'ncu -i {rep} --page source --csv > /tmp/src.csv 2>/dev/null', shell=True)
 rows=list(csv.reader(open('/tmp/raw.csv'))); hdr=rows[0]; units=rows[1]

@@ -223,7 +223,9 @@ __device__ __forceinline__ void store_ref(float* dst, int j, const BodyState& r)
     st3(dst + 240 + 3 * j, r.w);
 }
 
-template <bool PACKED>
+// DEBUG_REF instantiates the optional ref_state_t / ref_state_t1 outputs (otherwise their predicated-off stores would still
+// take load/store issue slots in every lane).
+template <bool PACKED, bool DEBUG_REF>
 __global__ void __maxnreg__(ST_MAXREG) step_fused_kernel(const StepArgs a) {   // one persistent CTA per SM
     extern __shared__ float4 smem4[];
     float* tiles = reinterpret_cast<float*>(smem4);                          // [ST_TILES][S][934]
@@ -320,7 +322,7 @@ __global__ void __maxnreg__(ST_MAXREG) step_fused_kernel(const StepArgs a) {   /
                     }
                     *reinterpret_cast<float4*>(rj) = make_float4(sp, sr, sv, sa);
                     *reinterpret_cast<float2*>(rj + 4) = make_float2(dist, power);
-                    if (out.ref_state_t) store_ref(out.ref_state_t + e * FRAME_F, j, ref);
+                    if (DEBUG_REF && out.ref_state_t) store_ref(out.ref_state_t + e * FRAME_F, j, ref);
                     float* o = my_tile;
                     if (j == 0) o[0] = root_p.z;                                          // common.py:40
                     self_obs_pos_rot_fma(body, root_p, hz, hw, hrot, j, o + 1 + 3 * (j - 1), o + 70 + 6 * j);   // vel / ang blocks: role B
@@ -368,7 +370,7 @@ __global__ void __maxnreg__(ST_MAXREG) step_fused_kernel(const StepArgs a) {   /
                 }
             } else if (valid) {
                 // ============ role B: imitation observation (reference at t+1) + self vel / ang-vel ===========
-                if (out.ref_state_t1) store_ref(out.ref_state_t1 + e * FRAME_F, j, ref);
+                if (DEBUG_REF && out.ref_state_t1) store_ref(out.ref_state_t1 + e * FRAME_F, j, ref);
                 self_obs_vel_ang_fma(body, hrot, my_tile + 214 + 3 * j, my_tile + 286 + 3 * j);
                 float* q = my_tile + OBS_SELF;
                 task_obs_body_fma(body, ref, root_p, hz, hw, hrot, q + 3 * j, q + 72 + 6 * j, q + 216 + 3 * j, q + 288 + 3 * j,
@@ -528,14 +530,17 @@ extern "C" int phc_step_fused(const phc_motion_tables* t, const phc_step_in* in,
     int dev = 0;
     cudaGetDevice(&dev);
     if (smem_dev != dev) {
-        cudaError_t e1 = cudaFuncSetAttribute(step_fused_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ST_SMEM);
-        cudaError_t e2 = cudaFuncSetAttribute(step_fused_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ST_SMEM);
-        if (e1 != cudaSuccess || e2 != cudaSuccess)
-            return fail((int)(e1 != cudaSuccess ? e1 : e2), "%s: cudaFuncSetAttribute(%zu B smem): %s", fn, ST_SMEM,
-                        cudaGetErrorString(e1 != cudaSuccess ? e1 : e2));
+        cudaError_t e = cudaFuncSetAttribute(step_fused_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ST_SMEM);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(step_fused_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ST_SMEM);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(step_fused_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ST_SMEM);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(step_fused_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ST_SMEM);
+        if (e != cudaSuccess) return fail((int)e, "%s: cudaFuncSetAttribute(%zu B smem): %s", fn, ST_SMEM, cudaGetErrorString(e));
         smem_dev = dev;
     }
-    if (packed) step_fused_kernel<true><<<grid, ST_THREADS, ST_SMEM, s>>>(a);
-    else step_fused_kernel<false><<<grid, ST_THREADS, ST_SMEM, s>>>(a);
+    const bool dbg = out->ref_state_t || out->ref_state_t1;
+    if (packed && !dbg) step_fused_kernel<true, false><<<grid, ST_THREADS, ST_SMEM, s>>>(a);
+    else if (packed) step_fused_kernel<true, true><<<grid, ST_THREADS, ST_SMEM, s>>>(a);
+    else if (!dbg) step_fused_kernel<false, false><<<grid, ST_THREADS, ST_SMEM, s>>>(a);
+    else step_fused_kernel<false, true><<<grid, ST_THREADS, ST_SMEM, s>>>(a);
     return check_launch(fn);
 }
