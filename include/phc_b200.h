@@ -168,6 +168,15 @@ int phc_im_reset(const int16_t *progress, phc_view rigid_body_pos, phc_view ref_
                  int enable_early_termination, const float *termination_distance, int use_mean,
                  int64_t N, int J, uint8_t *reset, uint8_t *terminated, phc_stream_t stream);
 
+/* build_amp_observations_smpl + dof_to_obs_smpl (common.py:179-267; "next" row f3, only used with use_amp_obs) without the
+ * shape / limb-weight pass-through columns.  Contiguous inputs: root_* [N,3|4], dof_pos / dof_vel [N,69], key_body_pos [N,K,3];
+ * dof_subset: device [3*num_joints] int64 indices into the 69-dof vector, or NULL = all 23 joints in order.
+ * obs: [N, obs_stride >= (root_height_obs?1:0) + 12 + 9*num_joints + 3*K]. */
+int phc_amp_obs_smpl(const float *root_pos, const float *root_rot, const float *root_vel, const float *root_ang_vel,
+                     const float *dof_pos, const float *dof_vel, const float *key_body_pos, const int64_t *dof_subset,
+                     int num_joints, int K, int local_root_obs, int root_height_obs, int upright, int64_t N, float *obs,
+                     int64_t obs_stride, phc_stream_t stream);
+
 /* ------------------------------------------------------------------------------------------- */
 /* The whole post-physics half of HumanoidPHC.step in ONE pass over HBM                          */
 /* (puffer_phc/envs/humanoid_phc.py:136-149: _compute_reward :1228-1303, _compute_reset          */

@@ -218,3 +218,16 @@ def gae(dones, values, rewards, gamma, gae_lambda):
     adv = np.empty_like(r)
     lib().phc_oracle_gae(_p(d), _p(v), _p(r), C.c_int64(r.shape[0]), C.c_float(gamma), C.c_float(gae_lambda), _p(adv))
     return adv
+
+
+def amp_obs(root_pos, root_rot, root_vel, root_ang_vel, dof_pos, dof_vel, key_body_pos, dof_subset=None,
+            local_root_obs=True, root_height_obs=True, upright=True):
+    a = [_f32(x) for x in (root_pos, root_rot, root_vel, root_ang_vel, dof_pos, dof_vel, key_body_pos)]
+    N, K = a[0].shape[0], a[6].shape[1]
+    sub = None if dof_subset is None else _i64(dof_subset)
+    nj = 23 if sub is None else sub.shape[0] // 3
+    W = (1 if root_height_obs else 0) + 12 + 9 * nj + 3 * K
+    obs = np.empty((N, W), np.float32)
+    lib().phc_oracle_amp_obs(*[_p(x) for x in a], _p(sub), C.c_int(nj), C.c_int(K), C.c_int(int(local_root_obs)),
+                             C.c_int(int(root_height_obs)), C.c_int(int(upright)), C.c_int64(N), _p(obs))
+    return obs

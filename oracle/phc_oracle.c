@@ -414,6 +414,63 @@ int phc_oracle_im_reset(const int16_t *progress, const float *body_pos, const fl
     return 0;
 }
 
+/* torch_utils.py:333-365 exp_map_to_quat = quat_from_angle_axis(exp_map_to_angle_axis(exp_map)) */
+static q4 o_exp_map_to_quat(v3 e)
+{
+    float angle = o_norm3(e);
+    v3 axis = { e.x / angle, e.y / angle, e.z / angle };
+    angle = o_normalize_angle(angle);
+    if (!(fabsf(angle) > 1e-5f)) { angle = 0.0f; axis.x = 0.0f; axis.y = 0.0f; axis.z = 1.0f; }
+    float th = angle / 2.0f;
+    float an = o_norm3(axis);                       /* normalize(axis): x / max(norm, 1e-9) (:44-46) */
+    if (an < 1e-9f) an = 1e-9f;
+    float sn = sinf(th);
+    float x = (axis.x / an) * sn, y = (axis.y / an) * sn, z = (axis.z / an) * sn, w = cosf(th);
+    float n = sqrtf(fmaf(w, w, fmaf(z, z, fmaf(y, y, x * x))));
+    if (n < 1e-9f) n = 1e-9f;
+    q4 r = { x / n, y / n, z / n, w / n };
+    return r;
+}
+
+/* common.py:192-267 build_amp_observations_smpl (+ dof_to_obs_smpl :179-189) without the shape / limb pass-through columns.
+ * dof_subset: 3*nj indices into the 69-dof vector (or NULL = all 23 joints); key_body_pos [N,K,3].
+ * obs: [N, (root_height_obs?1:0) + 12 + 9*nj + 3*K]. */
+int phc_oracle_amp_obs(const float *root_pos, const float *root_rot, const float *root_vel, const float *root_ang,
+                       const float *dof_pos, const float *dof_vel, const float *key_pos, const int64_t *dof_subset, int nj,
+                       int K, int local_root_obs, int root_height_obs, int upright, int64_t N, float *obs)
+{
+    int W = (root_height_obs ? 1 : 0) + 12 + 9 * nj + 3 * K;
+    for (int64_t i = 0; i < N; ++i) {
+        float *o = obs + i * (int64_t)W;
+        q4 rr = ldq(root_rot + i * 4);
+        v3 rp = ldv(root_pos + i * 3);
+        if (!upright) rr = o_remove_base_rot(rr);                                   /* :214-215 */
+        q4 hinv = o_quat_from_angle_z(-o_heading(rr));                              /* :216 */
+        if (root_height_obs) *o++ = rp.z;                                           /* :213, 250-251 */
+        o_tan_norm(local_root_obs ? o_quat_mul(hinv, rr) : rr, o);                  /* :218-223 */
+        v3 v = o_quat_rotate(hinv, ldv(root_vel + i * 3));                          /* :225 */
+        v3 w = o_quat_rotate(hinv, ldv(root_ang + i * 3));                          /* :226 */
+        o[6] = v.x; o[7] = v.y; o[8] = v.z; o[9] = w.x; o[10] = w.y; o[11] = w.z;
+        float *dobs = o + 12, *dvel = dobs + 6 * nj, *kp = dvel + 3 * nj;
+        for (int j = 0; j < nj; ++j) {
+            v3 e;
+            float dv[3];
+            for (int c = 0; c < 3; ++c) {
+                int64_t idx = dof_subset ? dof_subset[3 * j + c] : 3 * j + c;       /* :244-246 */
+                ((float *)&e)[c] = dof_pos[i * 69 + idx];
+                dv[c] = dof_vel[i * 69 + idx];
+            }
+            o_tan_norm(o_exp_map_to_quat(e), dobs + 6 * j);                         /* :186, 248 */
+            dvel[3 * j] = dv[0]; dvel[3 * j + 1] = dv[1]; dvel[3 * j + 2] = dv[2];
+        }
+        for (int k = 0; k < K; ++k) {                                               /* :228-242 */
+            v3 d = o_quat_rotate(hinv, v3sub(ldv(key_pos + (i * K + k) * 3), rp));
+            kp[3 * k] = d.x; kp[3 * k + 1] = d.y; kp[3 * k + 2] = d.z;
+        }
+    }
+    return 0;
+}
+
 /* ------------------------------------------------------------------------------------ */
 /* The per-step glue of HumanoidPHC.step() after physics (puffer_phc/envs/humanoid_phc.py */
 /* :136-149): _compute_reward :1228-1303, _compute_reset :1311-1333,                      */

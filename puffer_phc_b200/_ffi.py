@@ -18,7 +18,7 @@ c_f32p, c_i64p, c_u8p, c_i16p, c_f64p = C.c_void_p, C.c_void_p, C.c_void_p, C.c_
 
 EXPORTS = (
     "phc_version", "phc_last_error", "phc_pack_frames", "phc_motion_state", "phc_reset_ref_state", "phc_sample_time_interval",
-    "phc_imitation_obs_v6", "phc_self_obs_smpl_max", "phc_imitation_reward", "phc_im_reset",
+    "phc_imitation_obs_v6", "phc_self_obs_smpl_max", "phc_amp_obs_smpl", "phc_imitation_reward", "phc_im_reset",
     "phc_step_num_partials", "phc_step_fused", "phc_rms_forward", "phc_rms_scratch_doubles", "phc_rms_moments",
     "phc_rms_reduce_partials", "phc_rms_finalize", "phc_gae",
 )
@@ -81,6 +81,7 @@ def _declare(lib):
     lib.phc_sample_time_interval.argtypes = [P, P, I64, I, P, P]
     lib.phc_imitation_obs_v6.argtypes = [View] * 10 + [I64, I, I, I, P, I64, P]
     lib.phc_self_obs_smpl_max.argtypes = [View] * 4 + [I64, I, I, I, I, P, I64, P]
+    lib.phc_amp_obs_smpl.argtypes = [P] * 8 + [I, I, I, I, I, I64, P, I64, P]
     lib.phc_imitation_reward.argtypes = [View] * 8 + [I64, I, C.POINTER(F), C.POINTER(F), P, P, I64, P]
     lib.phc_im_reset.argtypes = [P, View, View, P, I, P, I, I64, I, P, P, P]
     lib.phc_step_num_partials.argtypes, lib.phc_step_num_partials.restype = [], I

@@ -113,6 +113,46 @@ __global__ void __launch_bounds__(IM_WARPS * 32) reset_kernel(const ResetArgs a)
     }
 }
 
+// build_amp_observations_smpl + dof_to_obs_smpl (reference envs/common.py:179-267), "next" row f3.
+// One warp per env: lane j = dof joint j of the subset (exp-map -> quaternion -> tan-norm, and the dof velocity copy);
+// the root terms and the key-body positions are spread over the first lanes.
+struct AmpArgs {
+    const float *root_pos, *root_rot, *root_vel, *root_ang, *dof_pos, *dof_vel, *key_pos;
+    const int64_t* subset; int nj, K, local_root_obs, root_height_obs, upright; int64_t N; float* obs; int64_t obs_stride;
+};
+
+__global__ void __launch_bounds__(IM_WARPS * 32) amp_obs_kernel(const AmpArgs a) {
+    const int lane = threadIdx.x & 31;
+    const int64_t n = (int64_t)blockIdx.x * IM_WARPS + (threadIdx.x >> 5);
+    if (n >= a.N) return;
+    Q4 rr = ld4(a.root_rot + n * 4);
+    if (!a.upright) rr = remove_base_rot(rr);                                   // common.py:214-215
+    float hz, hw;
+    heading_quat(calc_heading(rr), hz, hw);                                     // h^-1 = (0,0,-hz,hw)  (:216)
+    const V3 rp = ld3(a.root_pos + n * 3);
+    float* o = a.obs + n * a.obs_stride;
+    if (a.root_height_obs) { if (lane == 0) o[0] = rp.z; o += 1; }              // :213, 250-251
+    if (lane == 0) tan_norm(a.local_root_obs ? quat_mul(Q4{0.0f, 0.0f, -hz, hw}, rr) : rr, o);   // :218-223
+    if (lane == 1) put3(o + 6, rotate_z(-hz, hw, ld3(a.root_vel + n * 3)));     // :225
+    if (lane == 2) put3(o + 9, rotate_z(-hz, hw, ld3(a.root_ang + n * 3)));     // :226
+    float* dobs = o + 12;
+    float* dvel = dobs + 6 * a.nj;
+    float* kp = dvel + 3 * a.nj;
+    for (int j = lane; j < a.nj; j += 32) {
+        float e[3], v[3];
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            const int64_t idx = a.subset ? __ldg(a.subset + 3 * j + c) : 3 * j + c;          // :244-246
+            e[c] = __ldg(a.dof_pos + n * NDOF + idx);
+            v[c] = __ldg(a.dof_vel + n * NDOF + idx);
+        }
+        tan_norm(exp_map_to_quat(V3{e[0], e[1], e[2]}), dobs + 6 * j);                        // :186, 248
+        dvel[3 * j] = v[0]; dvel[3 * j + 1] = v[1]; dvel[3 * j + 2] = v[2];
+    }
+    for (int k = lane; k < a.K; k += 32)                                                      // :228-242
+        put3(kp + 3 * k, rotate_z(-hz, hw, ld3(a.key_pos + (n * a.K + k) * 3) - rp));
+}
+
 static int check_view(const char* fn, const char* name, const phc_view& v) {
     if (!v.ptr) return fail(PHC_EINVAL, "%s: %s is NULL", fn, name);
     return PHC_OK;
@@ -156,6 +196,23 @@ extern "C" int phc_self_obs_smpl_max(phc_view body_pos, phc_view body_rot, phc_v
     PHC_REQUIRE(obs_stride >= (root_height_obs ? 1 : 0) + 3 * (J - 1) + 12 * J, PHC_ESHAPE, "%s: obs_stride too small", fn);
     SelfArgs a{body_pos, body_rot, body_vel, body_ang_vel, N, J, local_root_obs, root_height_obs, upright, obs, obs_stride};
     self_obs_kernel<<<(unsigned)((N + IM_WARPS - 1) / IM_WARPS), IM_WARPS * 32, 0, (cudaStream_t)stream>>>(a);
+    return check_launch(fn);
+}
+
+extern "C" int phc_amp_obs_smpl(const float* root_pos, const float* root_rot, const float* root_vel, const float* root_ang_vel,
+                                const float* dof_pos, const float* dof_vel, const float* key_body_pos, const int64_t* dof_subset,
+                                int num_joints, int K, int local_root_obs, int root_height_obs, int upright, int64_t N, float* obs,
+                                int64_t obs_stride, phc_stream_t stream) {
+    const char* fn = "phc_amp_obs_smpl";
+    PHC_REQUIRE(N >= 0, PHC_EINVAL, "%s: N < 0", fn);
+    PHC_REQUIRE(num_joints >= 0 && num_joints <= 23 && K >= 0, PHC_ESHAPE, "%s: num_joints=%d K=%d out of range", fn, num_joints, K);
+    if (N == 0) return PHC_OK;
+    PHC_REQUIRE(root_pos && root_rot && root_vel && root_ang_vel && dof_pos && dof_vel && (key_body_pos || K == 0) && obs, PHC_EINVAL,
+                "%s: NULL pointer", fn);
+    PHC_REQUIRE(obs_stride >= (root_height_obs ? 1 : 0) + 12 + 9 * num_joints + 3 * K, PHC_ESHAPE, "%s: obs_stride too small", fn);
+    AmpArgs a{root_pos, root_rot, root_vel, root_ang_vel, dof_pos, dof_vel, key_body_pos, dof_subset, num_joints, K, local_root_obs,
+              root_height_obs, upright, N, obs, obs_stride};
+    amp_obs_kernel<<<(unsigned)((N + IM_WARPS - 1) / IM_WARPS), IM_WARPS * 32, 0, (cudaStream_t)stream>>>(a);
     return check_launch(fn);
 }
 

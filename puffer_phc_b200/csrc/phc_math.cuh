@@ -274,6 +274,23 @@ PHC_HD Q4 slerp_rcp(Q4 q0, Q4 q1, float t) {
     return Q4{ra * q0.x + rb * q1.x, ra * q0.y + rb * q1.y, ra * q0.z + rb * q1.z, ra * q0.w + rb * q1.w};
 }
 
+// exp_map_to_quat (torch_utils.py:333-365) = quat_from_angle_axis(exp_map_to_angle_axis(e)); norms use the CPU reference's
+// fma chain, the small-angle mask falls back to angle 0 about (0,0,1).
+PHC_HD Q4 exp_map_to_quat(V3 e) {
+    float angle = sqrtf(fmaf(e.z, e.z, fmaf(e.y, e.y, e.x * e.x)));
+    V3 axis{e.x / angle, e.y / angle, e.z / angle};
+    angle = atan2f(sinf(angle), cosf(angle));                       // normalize_angle (:50-51)
+    if (!(fabsf(angle) > 1e-5f)) { angle = 0.0f; axis = V3{0.0f, 0.0f, 1.0f}; }
+    const float th = angle / 2.0f;
+    float an = sqrtf(fmaf(axis.z, axis.z, fmaf(axis.y, axis.y, axis.x * axis.x)));
+    if (an < 1e-9f) an = 1e-9f;
+    const float sn = sinf(th);
+    const float x = (axis.x / an) * sn, y = (axis.y / an) * sn, z = (axis.z / an) * sn, w = cosf(th);
+    float n = sqrtf(fmaf(w, w, fmaf(z, z, fmaf(y, y, x * x))));
+    if (n < 1e-9f) n = 1e-9f;
+    return Q4{x / n, y / n, z / n, w / n};
+}
+
 // lerp as written in get_motion_state (motion_lib.py:596-603): (1-b)*x0 + b*x1
 PHC_HD float lerp(float a, float b, float one_m, float t) { return one_m * a + t * b; }
 

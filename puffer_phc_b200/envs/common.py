@@ -61,6 +61,60 @@ def compute_humanoid_observations_smpl_max(body_pos, body_rot, body_vel, body_an
     return obs
 
 
+def dof_to_obs_smpl(pose):
+    """reference envs/common.py:179-189: exp-map triplets -> tan-norm, ``[B, 3*nj] -> [B, 6*nj]`` (through the AMP kernel)."""
+    B, jts = pose.shape
+    z3, z4 = pose.new_zeros(B, 3), pose.new_zeros(B, 4)
+    z4[:, 3] = 1
+    full = build_amp_observations_smpl(z3, z4, z3, z3, _pad69(pose), _pad69(pose), pose.new_zeros(B, 0, 3), pose.new_zeros(B, 0),
+                                       pose.new_zeros(B, 0), torch.arange(jts, device=pose.device), True, False, True, False, False, True)
+    return full[:, 12:12 + 2 * jts].contiguous()
+
+
+def _pad69(x):
+    if x.shape[1] == 69:
+        return x
+    out = x.new_zeros(x.shape[0], 69)
+    out[:, : x.shape[1]] = x
+    return out
+
+
+def build_amp_observations_smpl(root_pos, root_rot, root_vel, root_ang_vel, dof_pos, dof_vel, key_body_pos, shape_params,
+                                limb_weight_params, dof_subset, local_root_obs, root_height_obs, has_dof_subset, has_shape_obs_disc,
+                                has_limb_weight_obs, upright):
+    """reference envs/common.py:192-267 -> ``[B, (1) + 6 + 3 + 3 + 6*nj + 3*nj + 3*K (+ shape) (+ limb)]``."""
+    lib = _ffi.load()
+    _ffi.require_cuda(root_pos, root_rot, root_vel, root_ang_vel, dof_pos, dof_vel, key_body_pos)
+    ts = [t.to(torch.float32).contiguous() for t in (root_pos, root_rot, root_vel, root_ang_vel, dof_pos, dof_vel, key_body_pos)]
+    B, K = ts[0].shape[0], ts[6].shape[1]
+    if ts[4].shape[1] != 69 or ts[5].shape[1] != 69:
+        raise ValueError("build_amp_observations_smpl: dof_pos / dof_vel must be [B, 69] (23 SMPL joints)")
+    sub = None
+    nj = 23
+    if has_dof_subset:
+        sub = dof_subset.to(device=ts[0].device, dtype=torch.int64).contiguous()
+        if sub.numel() % 3:
+            raise ValueError("dof_subset must list whole joints (a multiple of 3 indices)")
+        nj = sub.numel() // 3
+    W = (1 if root_height_obs else 0) + 12 + 9 * nj + 3 * K
+    extra = []
+    if has_shape_obs_disc:
+        extra.append(shape_params)
+    if has_limb_weight_obs:
+        extra.append(limb_weight_params)
+    Wt = W + sum(int(x.shape[-1]) for x in extra)
+    obs = torch.empty((B, Wt), dtype=torch.float32, device=ts[0].device)
+    with torch.cuda.device(obs.device):
+        _ffi.check(lib.phc_amp_obs_smpl(*[_ffi.ptr(t) for t in ts], _ffi.ptr(sub), nj, K, int(bool(local_root_obs)),
+                                        int(bool(root_height_obs)), int(bool(upright)), B, _ffi.ptr(obs), obs.stride(0),
+                                        _ffi.stream_ptr()), "build_amp_observations_smpl")
+    col = W
+    for x in extra:
+        obs[:, col:col + x.shape[-1]] = x
+        col += x.shape[-1]
+    return obs
+
+
 def compute_imitation_reward(root_pos, root_rot, body_pos, body_rot, body_vel, body_ang_vel, ref_body_pos, ref_body_rot,
                              ref_body_vel, ref_body_ang_vel, rwd_specs: Dict[str, float]) -> Tuple[torch.Tensor, torch.Tensor]:
     """reference envs/common.py:270-322 -> ``(reward [B], reward_raw [B,4])``.  root_pos/root_rot are unused there too."""

@@ -59,3 +59,8 @@ def assert_equal(a, b, what=""):
 @pytest.fixture(scope="session")
 def golden():
     return {n: load_npz(n + ".npz") for n in ("cmu_tables", "cmu_step", "synth_tables", "synth_step", "gae", "rms", "sample_time")}
+
+
+@pytest.fixture(scope="session")
+def golden_amp():
+    return load_npz("amp.npz")

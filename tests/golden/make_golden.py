@@ -18,6 +18,7 @@ running its own torch (CPU, fp32) / Cython functions on seeded inputs and commit
   gae.npz           c_gae.compute_gae on 512x32 and edge cases (the reference .pyx compiled by oracle/Makefile)
   rms.npz           RunningNorm.update x2 + forward
   sample_time.npz   sample_time_interval / get_motion_num_steps arithmetic
+  amp.npz           build_amp_observations_smpl (AMP discriminator observation, off by default in the reference)
 
 The glue between the functions (motion_times, pass_time, obs concatenation, power reward) is restated
 from puffer_phc/envs/humanoid_phc.py at the lines cited below, because HumanoidPHC itself needs Isaac Gym.
@@ -168,13 +169,49 @@ def save(name, d):
     print(f"wrote {name}: {os.path.getsize(path) / 1e6:.2f} MB, {len(arrs)} arrays")
 
 
+def make_amp(common):
+    """AMP observations (row f3): build_amp_observations_smpl (envs/common.py:192-267) on the inputs of cmu_step.npz.
+    Reads the committed fixture, so it can be regenerated on its own (--only amp)."""
+    z = np.load(os.path.join(HERE, "cmu_step.npz"))
+    st = torch.from_numpy(z["in_body_state"])[:, :24]
+    root_pos, root_rot, root_vel, root_ang = st[:, 0, 0:3], st[:, 0, 3:7], st[:, 0, 7:10], st[:, 0, 10:13]
+    dof_pos, dof_vel = torch.from_numpy(z["t0_dof_pos"]), torch.from_numpy(z["t0_dof_vel"])
+    dof_pos = dof_pos + 0.05 * torch.randn(dof_pos.shape, generator=torch.Generator().manual_seed(21))
+    dof_pos[:8, 0:3] = 0.0                               # exercise the small-angle branch of exp_map_to_angle_axis
+    dof_pos[8:16, 3:6] = torch.tensor([0.0, 0.0, 4.0])   # angle > pi: normalize_angle wraps
+    key_ids = [7, 3, 21, 17]                             # R_Ankle, L_Ankle, R_Wrist, L_Wrist (body_sets.py:45)
+    key_pos = st[:, key_ids, 0:3]
+    joints = [j for j in range(23) if j not in (3, 7, 17, 22)]      # dof joints without toes / hands (humanoid_phc.py:186-196)
+    subset = torch.tensor([3 * j + k for j in joints for k in range(3)], dtype=torch.long)
+    shape = torch.randn(st.shape[0], 11, generator=torch.Generator().manual_seed(22))
+    limb = torch.rand(st.shape[0], 10, generator=torch.Generator().manual_seed(23))
+    out = {"root_pos": root_pos, "root_rot": root_rot, "root_vel": root_vel, "root_ang_vel": root_ang, "dof_pos": dof_pos,
+           "dof_vel": dof_vel, "key_pos": key_pos, "subset": subset, "shape": shape, "limb": limb}
+    variants = {  # local_root_obs, root_height_obs, has_dof_subset, has_shape_obs_disc, has_limb_weight_obs, upright
+        "default": (True, True, True, False, False, True),
+        "full_dof": (True, True, False, False, False, True),
+        "global_root": (False, False, True, False, False, True),
+        "not_upright": (True, True, True, False, False, False),
+        "with_params": (True, True, True, True, True, True),
+    }
+    for name, f in variants.items():
+        out[f"amp_{name}"] = common.build_amp_observations_smpl(root_pos, root_rot, root_vel, root_ang, dof_pos, dof_vel, key_pos,
+                                                                 shape, limb, subset, *f)
+        out[f"flags_{name}"] = np.array(f, dtype=np.int32)
+    save("amp.npz", out)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--ref", default="/root/reference")
+    ap.add_argument("--only", default=None, help="regenerate a single fixture (amp)")
     args = ap.parse_args()
     torch.set_num_threads(1)
     ml, common, SkeletonTree, rn = boot_reference(args.ref)
     from puffer_phc_b200 import synth
+    if args.only == "amp":
+        make_amp(common)
+        return
 
     # ---- config 1: the real clip -------------------------------------------------------------
     lib = load_cmu(ml, SkeletonTree, args.ref)
@@ -248,6 +285,7 @@ def main():
     torch.manual_seed(321)
     samp["phase_trunc"] = torch.rand(ids.shape)
     save("sample_time.npz", samp)
+    make_amp(common)
 
 
 if __name__ == "__main__":

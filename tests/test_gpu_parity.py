@@ -414,3 +414,18 @@ def test_running_norm_update_layouts():
         np.testing.assert_allclose(npy(rn.running_mean)[0], x64.mean(0), rtol=1e-6, atol=1e-7)
         np.testing.assert_allclose(npy(rn.running_var)[0], x64.var(0), rtol=1e-5, atol=1e-9)
         assert float(rn.count) == 2.0
+
+
+def test_amp_observations_vs_golden(golden_amp):
+    """build_amp_observations_smpl / dof_to_obs_smpl (row f3) against the reference's outputs."""
+    from puffer_phc_b200.envs import common
+    A = golden_amp
+    base = [cu(A[k]) for k in ("root_pos", "root_rot", "root_vel", "root_ang_vel", "dof_pos", "dof_vel", "key_pos")]
+    shape, limb, subset = cu(A["shape"]), cu(A["limb"]), cu(A["subset"])
+    for name in ("default", "full_dof", "global_root", "not_upright", "with_params"):
+        lro, rho, sub, shp, lw, up = (bool(x) for x in A[f"flags_{name}"])
+        got = common.build_amp_observations_smpl(*base, shape, limb, subset, lro, rho, sub, shp, lw, up)
+        assert tuple(got.shape) == A[f"amp_{name}"].shape
+        assert_close(npy(got), A[f"amp_{name}"], what=f"amp obs {name}", row_scale=True)
+    d = common.dof_to_obs_smpl(cu(A["dof_pos"])[:, A["subset"]])
+    assert_close(npy(d), A["amp_default"][:, 13:13 + 114], what="dof_to_obs_smpl", row_scale=True)

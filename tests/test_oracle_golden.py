@@ -138,3 +138,15 @@ def test_sample_time_interval(golden):
     assert_equal(t.view(np.uint32), S["time_interval"].view(np.uint32), "sample_time_interval bits (CPU semantics)")
     t = co.sample_time_interval(S["phase_trunc"], T["motion_len"][S["ids"]] - np.float32(0.1), div_mode=0)
     assert_equal(t.view(np.uint32), S["time_interval_trunc"].view(np.uint32), "truncate_time variant")
+
+
+def test_amp_observations(golden_amp):
+    A = golden_amp
+    base = (A["root_pos"], A["root_rot"], A["root_vel"], A["root_ang_vel"], A["dof_pos"], A["dof_vel"], A["key_pos"])
+    for name in ("default", "full_dof", "global_root", "not_upright", "with_params"):
+        lro, rho, sub, shp, limb, up = (bool(x) for x in A[f"flags_{name}"])
+        got = co.amp_obs(*base, A["subset"] if sub else None, lro, rho, up)
+        want = A[f"amp_{name}"]
+        assert_close(got, want[:, : got.shape[1]], what=f"amp obs {name}", row_scale=True)
+        if shp:      # pass-through columns
+            assert_equal(want[:, got.shape[1]:], np.concatenate([A["shape"], A["limb"]], -1), "shape/limb columns")
