@@ -86,6 +86,65 @@ typedef struct phc_motion_tables {
 int phc_pack_frames(const phc_motion_tables *t, float *packed, phc_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------- */
+/* Motion TABLE BUILD ("next" row f4): MotionLibSMPL.load_motion_with_skeleton                   */
+/* (puffer_phc/motion_lib.py:744-825) = SkeletonState.from_rotation_and_root_translation          */
+/* (is_local=False) + SkeletonMotion.from_skeleton_state (puffer_phc/poselib_skeleton.py:1167-   */
+/* 1249: forward kinematics, np.gradient + gaussian-filtered velocities) + compute_motion_dof_   */
+/* vels_jit (motion_lib.py:119-140), for all clips of a library in ONE launch, written straight  */
+/* into the concatenated tables of load_motions (motion_lib.py:405-412).  The reference's        */
+/* precision mix is reproduced: float64 rotations, float32 forward kinematics, float32 gradient, */
+/* double-accumulated gaussian filter (see oracle/loader_oracle.c).                              */
+/* Raw clips are in the pkl format of scripts/convert_amass_data.py:186-196, concatenated:       */
+/* pose_quat_global [Fin,J,4] float64 (GLOBAL rotations, xyzw), root_trans_offset [Fin,3]        */
+/* float64.  Clip m reads raw frames [in_start[m], in_start[m] + num_frames[m]) (the crop of     */
+/* motion_lib.py:773-785 is folded into in_start) and writes table rows                          */
+/* [out_start[m], out_start[m] + num_frames[m]).  num_frames[m] >= 2 (the reference raises on    */
+/* one-frame clips; the kernel writes zero velocities for them).                                 */
+/* ------------------------------------------------------------------------------------------- */
+#define PHC_BUILD_TILE 32 /* frames per CTA; tile_prefix counts ceil(num_frames / PHC_BUILD_TILE) per clip */
+
+typedef struct phc_build_in {
+    const double *pose_quat_global;  /* [Fin,J,4] float64, 16-byte aligned                                       */
+    const double *root_trans;        /* [Fin,3]   float64                                                        */
+    const int64_t *in_start;         /* [M] first raw frame of clip m (crop start included)                      */
+    const int64_t *num_frames;       /* [M] frames kept                                                          */
+    const int64_t *out_start;        /* [M] first table row of clip m (= length_starts, motion_lib.py:416-419)   */
+    const int32_t *fps;              /* [M] curr_file.get("fps", 30)                                             */
+    const int64_t *tile_prefix;      /* [M+1] exclusive prefix sum of ceil(num_frames / PHC_BUILD_TILE)          */
+    const int32_t *parents;          /* [J] SkeletonTree.parent_indices (-1 = root; parents precede children)    */
+    const float *local_translation;  /* [M or 1, J, 3] SkeletonTree.local_translation of skeleton_trees[m]       */
+    int64_t lt_clip_stride;          /* floats between the skeletons of consecutive clips; 0 = one shared tree   */
+    const double *heading;           /* optional [M]: random heading angle (rad) applied to rotations and root
+                                        translation before the build (motion_lib.py:789-799); NULL = none        */
+    int64_t M;
+    int64_t n_tiles;                 /* = tile_prefix[M] (the library never reads device memory on the host)     */
+    int J;                           /* bodies, 2..32                                                            */
+} phc_build_in;
+
+typedef struct phc_build_out {
+    float *gts;     /* [F,J,3] */
+    float *grs;     /* [F,J,4] 16-byte aligned */
+    float *lrs;     /* [F,J,4] 16-byte aligned */
+    float *gvs;     /* [F,J,3] */
+    float *gavs;    /* [F,J,3] */
+    float *dvs;     /* [F,J-1,3] */
+    float *packed;  /* optional [F,312] (J == 24 only): the frame records of phc_pack_frames, written in the same pass */
+} phc_build_out;
+
+int phc_build_motion_tables(const phc_build_in *in, const phc_build_out *out, phc_stream_t stream);
+
+/* _motion_aa (motion_lib.py:381, 399): slot s contributes the float64 pose_aa rows of its WHOLE clip (the reference appends
+ * the uncropped array): raw rows [seg_src[s], seg_src[s] + len_s) -> float32 table rows [seg_dst_prefix[s], seg_dst_prefix[s+1]).
+ * heading (optional [S], with crop_lo / crop_hi [S] = the crop relative to the clip): the root rotation vector of the rows
+ * inside the crop becomes (h * from_rotvec(rv)).as_rotvec() (motion_lib.py:793). */
+int phc_build_motion_aa(const double *pose_aa, int row_len, const int64_t *seg_src, const int64_t *seg_dst_prefix, int64_t S,
+                        int64_t n_rows, const double *heading, const int64_t *crop_lo, const int64_t *crop_hi, float *out,
+                        phc_stream_t stream);
+
+/* plain float64 -> float32 cast of n elements */
+int phc_cast_f64_f32(const double *x, int64_t n, float *y, phc_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------- */
 /* MotionLibBase.get_motion_state(motion_ids, motion_times, offset=None)                        */
 /* (puffer_phc/motion_lib.py:549-626) and get_root_pos_smpl (:628-653).                         */
 /* Any output pointer may be NULL (that output is skipped); get_root_pos_smpl = only root_pos.  */

@@ -29,9 +29,9 @@ TABLE_KEYS = ("gts", "grs", "lrs", "gvs", "gavs", "dvs", "motion_aa", "motion_le
 
 
 def build(force: bool = False) -> str:
-    """Compile oracle/phc_oracle.c -> oracle/_build/libphc_oracle.so (gcc, -ffp-contract=off)."""
-    src = os.path.join(_HERE, "phc_oracle.c")
-    if force or not os.path.isfile(_SO) or os.path.getmtime(_SO) < os.path.getmtime(src):
+    """Compile oracle/phc_oracle.c + loader_oracle.c -> oracle/_build/libphc_oracle.so (gcc, -ffp-contract=off)."""
+    srcs = [os.path.join(_HERE, f) for f in ("phc_oracle.c", "loader_oracle.c")]
+    if force or not os.path.isfile(_SO) or os.path.getmtime(_SO) < max(os.path.getmtime(s) for s in srcs):
         subprocess.check_call(["make", "-s", "-C", _HERE, "CC=gcc"])
     return _SO
 
@@ -231,3 +231,19 @@ def amp_obs(root_pos, root_rot, root_vel, root_ang_vel, dof_pos, dof_vel, key_bo
     lib().phc_oracle_amp_obs(*[_p(x) for x in a], _p(sub), C.c_int(nj), C.c_int(K), C.c_int(int(local_root_obs)),
                              C.c_int(int(root_height_obs)), C.c_int(int(upright)), C.c_int64(N), _p(obs))
     return obs
+
+
+def build_clip(pose_quat_global, root_trans, parents, local_translation, fps):
+    """Motion table build for one (already cropped) clip -- oracle/loader_oracle.c.  Inputs float64 as in the pkl format;
+    returns the float32 per-clip table slices dict(gts, grs, lrs, gvs, gavs, dvs)."""
+    q = np.ascontiguousarray(pose_quat_global, dtype=np.float64)
+    tr = np.ascontiguousarray(root_trans, dtype=np.float64)
+    T, J = q.shape[0], q.shape[1]
+    par, lt = _i64(parents), _f32(local_translation)
+    out = dict(gts=np.empty((T, J, 3), np.float32), grs=np.empty((T, J, 4), np.float32), lrs=np.empty((T, J, 4), np.float32),
+               gvs=np.empty((T, J, 3), np.float32), gavs=np.empty((T, J, 3), np.float32), dvs=np.empty((T, J - 1, 3), np.float32))
+    rc = lib().phc_oracle_build_clip(_p(q), _p(tr), C.c_int64(T), C.c_int(J), _p(par), _p(lt), C.c_int(int(fps)),
+                                     *[_p(out[k]) for k in ("gts", "grs", "lrs", "gvs", "gavs", "dvs")])
+    if rc != 0:
+        raise ValueError(f"phc_oracle_build_clip failed ({rc}): clips need at least 2 frames")
+    return out

@@ -20,7 +20,7 @@ EXPORTS = (
     "phc_version", "phc_last_error", "phc_pack_frames", "phc_motion_state", "phc_reset_ref_state", "phc_sample_time_interval",
     "phc_imitation_obs_v6", "phc_self_obs_smpl_max", "phc_amp_obs_smpl", "phc_imitation_reward", "phc_im_reset",
     "phc_step_num_partials", "phc_step_fused", "phc_rms_forward", "phc_rms_scratch_doubles", "phc_rms_moments",
-    "phc_rms_reduce_partials", "phc_rms_finalize", "phc_gae",
+    "phc_rms_reduce_partials", "phc_rms_finalize", "phc_gae", "phc_build_motion_tables", "phc_build_motion_aa", "phc_cast_f64_f32",
 )
 
 PHC_OK, PHC_EINVAL, PHC_EALIGN, PHC_ESHAPE, PHC_EUNSUPPORTED = 0, -1, -2, -3, -4
@@ -71,6 +71,20 @@ class StepOut(C.Structure):
     ]
 
 
+class BuildIn(C.Structure):
+    """phc_build_in (raw clips -> tables, row f4)."""
+    _fields_ = [(k, C.c_void_p) for k in ("pose_quat_global", "root_trans", "in_start", "num_frames", "out_start", "fps",
+                                          "tile_prefix", "parents", "local_translation")] + \
+               [("lt_clip_stride", C.c_int64), ("heading", C.c_void_p), ("M", C.c_int64), ("n_tiles", C.c_int64), ("J", C.c_int)]
+
+
+class BuildOut(C.Structure):
+    _fields_ = [(k, C.c_void_p) for k in ("gts", "grs", "lrs", "gvs", "gavs", "dvs", "packed")]
+
+
+BUILD_TILE = 32     # PHC_BUILD_TILE
+
+
 def _declare(lib):
     P, I64, I, F = C.c_void_p, C.c_int64, C.c_int, C.c_float
     lib.phc_version.argtypes, lib.phc_version.restype = [], I
@@ -92,6 +106,9 @@ def _declare(lib):
     lib.phc_rms_reduce_partials.argtypes = [P, I, I64, I, P, P]
     lib.phc_rms_finalize.argtypes = [P, I, P, P, P, P]
     lib.phc_gae.argtypes = [P, P, P, I64, F, F, P, I, P]
+    lib.phc_build_motion_tables.argtypes = [C.POINTER(BuildIn), C.POINTER(BuildOut), P]
+    lib.phc_build_motion_aa.argtypes = [P, I, P, P, I64, I64, P, P, P, P, P]
+    lib.phc_cast_f64_f32.argtypes = [P, I64, P, P]
     for name in EXPORTS:
         fn = getattr(lib, name)
         if fn.restype is C.c_int and name not in ("phc_version", "phc_step_num_partials"):

@@ -19,6 +19,7 @@ running its own torch (CPU, fp32) / Cython functions on seeded inputs and commit
   rms.npz           RunningNorm.update x2 + forward
   sample_time.npz   sample_time_interval / get_motion_num_steps arithmetic
   amp.npz           build_amp_observations_smpl (AMP discriminator observation, off by default in the reference)
+  loader.npz        raw clips (the sample clip + three synthetic ones) and the tables load_motions builds from them
 
 The glue between the functions (motion_times, pass_time, obs concatenation, power reward) is restated
 from puffer_phc/envs/humanoid_phc.py at the lines cited below, because HumanoidPHC itself needs Isaac Gym.
@@ -201,16 +202,79 @@ def make_amp(common):
     save("amp.npz", out)
 
 
+def make_loader(ml, SkeletonTree, ref):
+    """Motion table build (row f4): raw clips in the on-disk format of scripts/convert_amass_data.py:186-196 and the tables
+    the reference loader (load_motions / load_motion_with_skeleton, motion_lib.py:257-429, 744-825) builds from them:
+    the real sample clip plus three synthetic clips (one longer than max_length, one at 60 fps)."""
+    import joblib
+    from puffer_phc_b200 import synth
+    sk = SkeletonTree.from_mjcf(f"{ref}/puffer_phc/assets/smpl_humanoid.xml")
+    raw = joblib.load(f"{ref}/sample_data/cmu_mocap_05_06.pkl")
+    clips = [raw[k] for k in raw]
+    T = synth.make_motion_library(3, seed=31, min_frames=20, max_frames=60, median_frames=45.0, other_fps_fraction=0.0, freeze_every=2)
+    for m in range(3):
+        a, n = int(T["length_starts"][m]), int(T["num_frames"][m])
+        clips.append({"root_trans_offset": T["gts"][a:a + n, 0].double().clone(), "pose_aa": T["motion_aa"][a:a + n].double().numpy(),
+                      "pose_quat_global": T["grs"][a:a + n].double().numpy(), "beta": np.zeros(16), "gender": "neutral",
+                      "fps": 60 if m == 2 else 30})
+    max_length = 50
+    cfg = SimpleNamespace(motion_file="", device="cpu", fix_height=ml.FixHeightMode.no_fix, min_length=5, max_length=max_length,
+                          im_eval=False, num_thread=1, smpl_type="smpl", step_dt=DT, is_deterministic=True)
+    lib = object.__new__(ml.MotionLibSMPL)
+    lib.m_cfg, lib._device, lib._sim_fps, lib.mesh_parsers = cfg, "cpu", 1 / DT, None
+    lib._motion_data_list = np.array(clips, dtype=object)
+    lib._motion_data_keys = np.array([f"clip{i}" for i in range(len(clips))])
+    lib._num_unique_motions = len(clips)
+    lib.setup_constants(fix_height=ml.FixHeightMode.no_fix, num_thread=1)
+    M = len(clips)
+    lib.load_motions(skeleton_trees=[sk] * M, gender_betas=torch.zeros(M, 17), limb_weights=np.zeros((M, 10)), random_sample=False)
+    out = {f"tab_{k}": v for k, v in tables_of(lib).items()}
+    out["max_length"] = np.array(max_length)
+    out["parents"] = sk.parent_indices.numpy()
+    out["local_translation"] = sk.local_translation.numpy()
+    for i, c in enumerate(clips):
+        out[f"clip{i}_root_trans_offset"] = np.asarray(c["root_trans_offset"], dtype=np.float64)
+        out[f"clip{i}_pose_aa"] = np.asarray(c["pose_aa"], dtype=np.float64)
+        out[f"clip{i}_pose_quat_global"] = np.asarray(c["pose_quat_global"], dtype=np.float64)
+        out[f"clip{i}_fps"] = np.array(c["fps"])
+    # ---- the non-deterministic path: random crop start (random.randint) and random heading (np.random.random, scipy
+    # Rotation) per clip, motion_lib.py:773-799.  The reference rotates pose_aa IN PLACE through a numpy view, so it runs
+    # on deep copies; the seeds are part of the fixture.
+    import copy
+    import random
+    clips_rnd = copy.deepcopy(clips)
+    cfg_rnd = SimpleNamespace(**{**vars(cfg), "is_deterministic": False})
+    lib_rnd = object.__new__(ml.MotionLibSMPL)
+    lib_rnd.m_cfg, lib_rnd._device, lib_rnd._sim_fps, lib_rnd.mesh_parsers = cfg_rnd, "cpu", 1 / DT, None
+    lib_rnd._motion_data_list = np.array(clips_rnd, dtype=object)
+    lib_rnd._motion_data_keys = np.array([f"clip{i}" for i in range(len(clips))])
+    lib_rnd._num_unique_motions = len(clips)
+    lib_rnd.setup_constants(fix_height=ml.FixHeightMode.no_fix, num_thread=1)
+    random.seed(7)
+    np.random.seed(7)
+    lib_rnd.load_motions(skeleton_trees=[sk] * M, gender_betas=torch.zeros(M, 17), limb_weights=np.zeros((M, 10)),
+                         random_sample=False, sample_idxes=torch.arange(M))
+    out.update({f"rnd_{k}": v for k, v in tables_of(lib_rnd).items()})
+    out["rnd_seed"] = np.array(7)
+    arrs = {k: (v.detach().cpu().numpy() if torch.is_tensor(v) else np.asarray(v)) for k, v in out.items()}
+    path = os.path.join(HERE, "loader.npz")
+    np.savez_compressed(path, **arrs)                      # keeps float64 inputs (save() would cast them to float32)
+    print(f"wrote loader.npz: {os.path.getsize(path) / 1e6:.2f} MB, {len(arrs)} arrays")
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--ref", default="/root/reference")
-    ap.add_argument("--only", default=None, help="regenerate a single fixture (amp)")
+    ap.add_argument("--only", default=None, help="regenerate a single fixture (amp | loader)")
     args = ap.parse_args()
     torch.set_num_threads(1)
     ml, common, SkeletonTree, rn = boot_reference(args.ref)
     from puffer_phc_b200 import synth
     if args.only == "amp":
         make_amp(common)
+        return
+    if args.only == "loader":
+        make_loader(ml, SkeletonTree, args.ref)
         return
 
     # ---- config 1: the real clip -------------------------------------------------------------
@@ -286,6 +350,7 @@ def main():
     samp["phase_trunc"] = torch.rand(ids.shape)
     save("sample_time.npz", samp)
     make_amp(common)
+    make_loader(ml, SkeletonTree, args.ref)
 
 
 if __name__ == "__main__":
