@@ -1,10 +1,14 @@
 """Summarise an ncu report of the fused step kernel: key raw metrics, stall-reason shares, and dynamic instruction counts
 per CUDA source line (SASS offsets from ncu --page source joined with nvdisasm -g line info of the in-tree library).
 
-    python profiles/tools/ncu_summary.py gpurun_out/<report>.ncu-rep [kernel-mangled-substring]
+    python profiles/tools/ncu_summary.py gpurun_out/<report>.ncu-rep [mangled-symbol-after-.text.] [cubin-stem] [units-per-launch]
+
+e.g. ... r1_loader_full.ncu-rep _ZN3phc19build_tables_kernel build_tables 2478461   (per-frame counts for the table build)
 """
 import csv, collections, re, sys, subprocess, glob
-rep=sys.argv[1]; kern=sys.argv[2] if len(sys.argv)>2 else 'step_fused_kernelILb1ELb0'
+rep=sys.argv[1]; kern=sys.argv[2] if len(sys.argv)>2 else '_ZN3phc17step_fused_kernelILb1ELb0'
+cubin=sys.argv[3] if len(sys.argv)>3 else 'step_fused'
+N=int(sys.argv[4]) if len(sys.argv)>4 else 65536
 subprocess.run(f'ncu -i {rep} --page raw --csv > /tmp/raw.csv 2>/dev/null', shell=True)
 subprocess.run(f'ncu -i {rep} --page source --csv > /tmp/src.csv 2>/dev/null', shell=True)
 rows=list(csv.reader(open('/tmp/raw.csv'))); hdr=rows[0]; units=rows[1]
@@ -13,9 +17,9 @@ r=rows[2]
 for w in want:
     if w in hdr: i=hdr.index(w); print(f'{w:70s} {r[i]} {units[i]}')
 # sass
-subprocess.run('rm -rf /tmp/cub; mkdir -p /tmp/cub; cd /tmp/cub; cuobjdump -xelf all /root/repo/puffer_phc_b200/lib/libphc_b200.so >/dev/null 2>&1; nvdisasm -g -c step_fused.sm_100a.cubin > /tmp/step_sass.txt', shell=True)
+subprocess.run('rm -rf /tmp/cub; mkdir -p /tmp/cub; cd /tmp/cub; cuobjdump -xelf all /root/repo/puffer_phc_b200/lib/libphc_b200.so >/dev/null 2>&1; nvdisasm -g -c '+cubin+'.sm_100a.cubin > /tmp/step_sass.txt', shell=True)
 lines=open('/tmp/step_sass.txt').read().split('\n')
-start=[i for i,l in enumerate(lines) if l.startswith('.text._ZN3phc17'+kern)][0]
+start=[i for i,l in enumerate(lines) if l.startswith('.text.'+kern)][0]
 off2src={}; cur=None
 for l in lines[start+1:]:
     if l.startswith('.text.') : break
@@ -41,8 +45,7 @@ for r in data:
     for i,h in stall_cols:
         try: st[h]+=int(r[i])
         except: pass
-N=65536
-print('total warp-instr/env', tot/N)
+print('total warp-instr/unit', tot/N)
 ss=sum(st.values())
 print('stalls:', ', '.join(f'{h[6:]} {100*c/ss:.1f}%' for h,c in st.most_common(9)))
 ts=sum(samp.values())
