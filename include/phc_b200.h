@@ -227,6 +227,10 @@ int phc_im_reset(const int16_t *progress, phc_view rigid_body_pos, phc_view ref_
                  int enable_early_termination, const float *termination_distance, int use_mean,
                  int64_t N, int J, uint8_t *reset, uint8_t *terminated, phc_stream_t stream);
 
+/* The evaluation metric HumanoidPHC.step adds when flag_im_eval is set (puffer_phc/envs/humanoid_phc.py:159-163, consumed by
+ * EvalStats, scripts/train.py:139-166): mpjpe[n] = mean_j || body_pos[n,j] - ref_body_pos[n,j] ||, ref = rg_pos at t. */
+int phc_mpjpe(phc_view body_pos, phc_view ref_body_pos, int64_t N, int J, float *mpjpe, phc_stream_t stream);
+
 /* build_amp_observations_smpl + dof_to_obs_smpl (common.py:179-267; "next" row f3, only used with use_amp_obs) without the
  * shape / limb-weight pass-through columns.  Contiguous inputs: root_* [N,3|4], dof_pos / dof_vel [N,69], key_body_pos [N,K,3];
  * dof_subset: device [3*num_joints] int64 indices into the 69-dof vector, or NULL = all 23 joints in order.

@@ -247,3 +247,10 @@ def build_clip(pose_quat_global, root_trans, parents, local_translation, fps):
     if rc != 0:
         raise ValueError(f"phc_oracle_build_clip failed ({rc}): clips need at least 2 frames")
     return out
+
+
+def mpjpe(body_pos, ref_body_pos):
+    bp, rp = _f32(body_pos), _f32(ref_body_pos)
+    out = np.empty(bp.shape[0], np.float32)
+    lib().phc_oracle_mpjpe(_p(bp), _p(rp), C.c_int64(bp.shape[0]), C.c_int(bp.shape[1]), _p(out))
+    return out

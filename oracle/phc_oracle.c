@@ -414,6 +414,17 @@ int phc_oracle_im_reset(const int16_t *progress, const float *body_pos, const fl
     return 0;
 }
 
+/* humanoid_phc.py:159-163: extras["mpjpe"] = (body_pos - rg_pos).norm(dim=-1).mean(dim=-1) */
+int phc_oracle_mpjpe(const float *body_pos, const float *ref_pos, int64_t N, int J, float *out)
+{
+    for (int64_t i = 0; i < N; ++i) {
+        float s = 0.0f;
+        for (int j = 0; j < J; ++j) s += o_norm3(v3sub(ldv(body_pos + (i * J + j) * 3), ldv(ref_pos + (i * J + j) * 3)));
+        out[i] = s / (float)J;
+    }
+    return 0;
+}
+
 /* torch_utils.py:333-365 exp_map_to_quat = quat_from_angle_axis(exp_map_to_angle_axis(exp_map)) */
 static q4 o_exp_map_to_quat(v3 e)
 {

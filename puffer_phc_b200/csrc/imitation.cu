@@ -113,6 +113,20 @@ __global__ void __launch_bounds__(IM_WARPS * 32) reset_kernel(const ResetArgs a)
     }
 }
 
+// Evaluation metric of HumanoidPHC.step (reference puffer_phc/envs/humanoid_phc.py:159-163):
+// mpjpe = (body_pos - rg_pos).norm(dim=-1).mean(dim=-1).  One warp per env, lane = body.
+struct MpjpeArgs { phc_view pos, rpos; int64_t N; int J; float* out; };
+
+__global__ void __launch_bounds__(IM_WARPS * 32) mpjpe_kernel(const MpjpeArgs a) {
+    const int lane = threadIdx.x & 31;
+    const int64_t n = (int64_t)blockIdx.x * IM_WARPS + (threadIdx.x >> 5);
+    if (n >= a.N) return;
+    float d = 0.0f;
+    if (lane < a.J) d = norm3(ld3(at(a.pos, n, lane)) - ld3(at(a.rpos, n, lane)));
+    d = warp_sum(d);
+    if (lane == 0) a.out[n] = d / (float)a.J;
+}
+
 // build_amp_observations_smpl + dof_to_obs_smpl (reference envs/common.py:179-267), "next" row f3.
 // One warp per env: lane j = dof joint j of the subset (exp-map -> quaternion -> tan-norm, and the dof velocity copy);
 // the root terms and the key-body positions are spread over the first lanes.
@@ -247,5 +261,17 @@ extern "C" int phc_im_reset(const int16_t* progress, phc_view rigid_body_pos, ph
     ResetArgs a{progress, rigid_body_pos, ref_body_pos, pass_time, enable_early_termination, termination_distance, use_mean,
                 N, J, reset, terminated};
     reset_kernel<<<(unsigned)((N + IM_WARPS - 1) / IM_WARPS), IM_WARPS * 32, 0, (cudaStream_t)stream>>>(a);
+    return check_launch(fn);
+}
+
+extern "C" int phc_mpjpe(phc_view body_pos, phc_view ref_body_pos, int64_t N, int J, float* mpjpe, phc_stream_t stream) {
+    const char* fn = "phc_mpjpe";
+    PHC_REQUIRE(N >= 0, PHC_EINVAL, "%s: N < 0", fn);
+    PHC_REQUIRE(J >= 1 && J <= 32, PHC_ESHAPE, "%s: J=%d outside [1,32]", fn, J);
+    if (N == 0) return PHC_OK;
+    CHECK_VIEW(fn, body_pos); CHECK_VIEW(fn, ref_body_pos);
+    PHC_REQUIRE(mpjpe, PHC_EINVAL, "%s: NULL pointer", fn);
+    MpjpeArgs a{body_pos, ref_body_pos, N, J, mpjpe};
+    mpjpe_kernel<<<(unsigned)((N + IM_WARPS - 1) / IM_WARPS), IM_WARPS * 32, 0, (cudaStream_t)stream>>>(a);
     return check_launch(fn);
 }

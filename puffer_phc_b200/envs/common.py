@@ -153,3 +153,15 @@ def compute_humanoid_im_reset(reset_buf, progress_buf, contact_buf, contact_body
     if reset_buf.dtype != torch.bool:
         reset, term = reset.to(reset_buf.dtype), term.to(reset_buf.dtype)
     return reset, term
+
+
+def compute_mpjpe(rigid_body_pos, ref_body_pos):
+    """``(body_pos - rg_pos).norm(dim=-1).mean(dim=-1)`` -- the per-env evaluation error HumanoidPHC.step puts in
+    ``extras["mpjpe"]`` when ``flag_im_eval`` is set (reference envs/humanoid_phc.py:159-163; EvalStats, scripts/train.py:139-166)."""
+    lib = _ffi.load()
+    pos, ref = _prep(rigid_body_pos, ref_body_pos)
+    B, J = pos.shape[0], pos.shape[1]
+    out = torch.empty(B, dtype=torch.float32, device=pos.device)
+    with torch.cuda.device(pos.device):
+        _ffi.check(lib.phc_mpjpe(_ffi.view3(pos), _ffi.view3(ref), B, J, _ffi.ptr(out), _ffi.stream_ptr()), "compute_mpjpe")
+    return out

@@ -93,11 +93,28 @@ class FusedStep:
         self.termination_distances[:] = d
 
     def __call__(self, body_state, progress_buf, motion_start_times, motion_start_times_offset, sampled_motion_ids,
-                 global_offset, dof_force=None, dof_vel=None, out: Optional[Dict[str, torch.Tensor]] = None) -> Dict[str, torch.Tensor]:
+                 global_offset, dof_force=None, dof_vel=None, out: Optional[Dict[str, torch.Tensor]] = None,
+                 env_range: Optional[Sequence[int]] = None) -> Dict[str, torch.Tensor]:
         """Run the step.  ``body_state`` is the PhysX rigid-body tensor ``[N, bodies_per_env, 13]`` (or ``[N, S]``);
-        returns the dict of output buffers (owned by this object unless ``out`` supplies them)."""
+        returns the dict of output buffers (owned by this object unless ``out`` supplies them).  ``env_range = (lo, hi)``
+        (both multiples of 8) restricts the launch to those envs of the same buffers (used to pipeline host transfers)."""
         _ffi.require_cuda(body_state, progress_buf, motion_start_times, motion_start_times_offset, sampled_motion_ids, global_offset)
-        N = self.N
+        if env_range is not None:
+            lo, hi = int(env_range[0]), int(env_range[1])
+            if not (0 <= lo < hi <= self.N) or lo % 8 or (hi % 8 and hi != self.N):
+                raise ValueError(f"env_range {env_range}: need 0 <= lo < hi <= {self.N}, multiples of 8")
+            sl = lambda t: None if t is None else t[lo:hi]          # noqa: E731
+            o = out or {}
+            sub = {k: sl(o.get(k, d)) for k, d in (("obs", self.obs_buf), ("obs_norm", self.obs_norm), ("reward", self.rew_buf),
+                                                   ("reward_raw", self.reward_raw), ("reset", self.reset_buf), ("terminated", self.terminate_buf))}
+            return self._run(hi - lo, body_state.reshape(self.N, -1)[lo:hi], sl(progress_buf), sl(motion_start_times),
+                             sl(motion_start_times_offset), sl(sampled_motion_ids), sl(global_offset), sl(dof_force), sl(dof_vel),
+                             sub, lo)
+        return self._run(self.N, body_state, progress_buf, motion_start_times, motion_start_times_offset, sampled_motion_ids,
+                         global_offset, dof_force, dof_vel, out, 0)
+
+    def _run(self, N, body_state, progress_buf, motion_start_times, motion_start_times_offset, sampled_motion_ids, global_offset,
+             dof_force, dof_vel, out, row0):
         for name, t, dt in (("progress_buf", progress_buf, torch.int16), ("motion_start_times", motion_start_times, torch.float32),
                             ("motion_start_times_offset", motion_start_times_offset, torch.float32),
                             ("sampled_motion_ids", sampled_motion_ids, torch.int64), ("global_offset", global_offset, torch.float32),
@@ -127,7 +144,8 @@ class FusedStep:
         sout = _ffi.StepOut(
             obs.data_ptr(), obs.stride(0), obs_norm.data_ptr() if self.normalize else None, rew.data_ptr(), raw.data_ptr(),
             raw.stride(0), reset.data_ptr(), term.data_ptr(), self.partials.data_ptr() if self.accumulate_moments else None,
-            self.ref_t.data_ptr() if self.ref_t is not None else None, self.ref_t1.data_ptr() if self.ref_t1 is not None else None)
+            self.ref_t[row0:].data_ptr() if self.ref_t is not None else None,
+            self.ref_t1[row0:].data_ptr() if self.ref_t1 is not None else None)
         with torch.cuda.device(self.device):
             _ffi.check(self.lib.phc_step_fused(C.byref(self.motion_lib.ctables), C.byref(sin), C.byref(self._ccfg), C.byref(sout),
                                                _ffi.stream_ptr()), "phc_step_fused")
@@ -141,10 +159,13 @@ class FusedStep:
     # ---- host-buffer entry (end-to-end path): H2D of the per-env inputs, the kernel, D2H of reward / flags ------------
     _HOST_KEYS = ("body_state", "progress", "start_time", "start_offset", "motion_ids", "global_offset", "dof_force", "dof_vel")
 
-    def step_host(self, host: Dict[str, torch.Tensor]) -> Dict[str, torch.Tensor]:
+    def step_host(self, host: Dict[str, torch.Tensor], chunks: int = 4) -> Dict[str, torch.Tensor]:
         """Same step with HOST (ideally pinned) input tensors, as a simulator living on the host would hand them over.
         Returns host tensors ``reward, reward_raw, reset, terminated`` (valid on return); the observation buffers stay on
-        the device for the policy (``self.obs_buf`` / ``self.obs_norm``)."""
+        the device for the policy (``self.obs_buf`` / ``self.obs_norm``).
+
+        The envs are processed in ``chunks`` ranges: the H2D copy of range c+1 (copy stream) runs under the kernel of range c
+        (compute stream) and the D2H of range c-1 (second copy stream), so only the PCIe transfer of the inputs is exposed."""
         keys = [k for k in self._HOST_KEYS if k in host and (self.cfg.use_power_reward or not k.startswith("dof_"))]
         if not hasattr(self, "_dev_in"):
             self._dev_in = {k: torch.empty(host[k].shape, dtype=host[k].dtype, device=self.device) for k in keys}
@@ -157,13 +178,29 @@ class FusedStep:
         for k in keys:
             if host[k].is_cuda:
                 raise RuntimeError("step_host expects host tensors; use __call__ for device-resident inputs")
-            self._dev_in[k].copy_(host[k], non_blocking=True)
-        d = self._dev_in
-        out = self(d["body_state"], d["progress"], d["start_time"], d["start_offset"], d["motion_ids"], d["global_offset"],
-                   d.get("dof_force"), d.get("dof_vel"))
-        for k, v in self._host_out.items():
-            v.copy_(out[k], non_blocking=True)
-        torch.cuda.current_stream(self.device).synchronize()
+        if not hasattr(self, "_h2d_stream"):
+            self._h2d_stream, self._d2h_stream = torch.cuda.Stream(device=self.device), torch.cuda.Stream(device=self.device)
+        d, N = self._dev_in, self.N
+        chunks = max(1, min(int(chunks), N // 8)) if N >= 8 else 1
+        per = -(-N // chunks)
+        per += (-per) % 8
+        main = torch.cuda.current_stream(self.device)
+        self._h2d_stream.wait_stream(main)              # earlier kernels may still read the staging buffers
+        self._d2h_stream.wait_stream(main)
+        for lo in range(0, N, per):
+            hi = min(lo + per, N)
+            with torch.cuda.stream(self._h2d_stream):
+                for k in keys:
+                    d[k][lo:hi].copy_(host[k][lo:hi], non_blocking=True)
+            main.wait_stream(self._h2d_stream)
+            out = self(d["body_state"], d["progress"], d["start_time"], d["start_offset"], d["motion_ids"], d["global_offset"],
+                       d.get("dof_force"), d.get("dof_vel"), env_range=(lo, hi))
+            self._d2h_stream.wait_stream(main)
+            with torch.cuda.stream(self._d2h_stream):
+                for k, v in self._host_out.items():
+                    v[lo:hi].copy_(out[k], non_blocking=True)
+        self._d2h_stream.synchronize()
+        main.synchronize()
         return self._host_out
 
     # ---- CUDA-graph replay: at small batch sizes the step is launch-bound (4096 envs = a few microseconds of GPU work) ------

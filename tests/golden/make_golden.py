@@ -19,6 +19,7 @@ running its own torch (CPU, fp32) / Cython functions on seeded inputs and commit
   rms.npz           RunningNorm.update x2 + forward
   sample_time.npz   sample_time_interval / get_motion_num_steps arithmetic
   amp.npz           build_amp_observations_smpl (AMP discriminator observation, off by default in the reference)
+  mpjpe.npz         extras["mpjpe"] of the evaluation step on both step fixtures
   loader.npz        raw clips (the sample clip + three synthetic ones) and the tables load_motions builds from them
 
 The glue between the functions (motion_times, pass_time, obs concatenation, power reward) is restated
@@ -202,6 +203,18 @@ def make_amp(common):
     save("amp.npz", out)
 
 
+def make_mpjpe():
+    """Evaluation error of HumanoidPHC.step (humanoid_phc.py:159-163): the reference's torch expression on the committed
+    sim states / reference positions of both step fixtures (--only mpjpe)."""
+    out = {}
+    for name in ("cmu_step", "synth_step"):
+        z = np.load(os.path.join(HERE, name + ".npz"))
+        body_pos = torch.from_numpy(z["in_body_state"])[:, :24, 0:3]
+        rg_pos = torch.from_numpy(z["t0_rg_pos"])
+        out[name] = (body_pos - rg_pos).norm(dim=-1).mean(dim=-1)
+    save("mpjpe.npz", out)
+
+
 def make_loader(ml, SkeletonTree, ref):
     """Motion table build (row f4): raw clips in the on-disk format of scripts/convert_amass_data.py:186-196 and the tables
     the reference loader (load_motions / load_motion_with_skeleton, motion_lib.py:257-429, 744-825) builds from them:
@@ -265,13 +278,16 @@ def make_loader(ml, SkeletonTree, ref):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--ref", default="/root/reference")
-    ap.add_argument("--only", default=None, help="regenerate a single fixture (amp | loader)")
+    ap.add_argument("--only", default=None, help="regenerate a single fixture (amp | loader | mpjpe)")
     args = ap.parse_args()
     torch.set_num_threads(1)
     ml, common, SkeletonTree, rn = boot_reference(args.ref)
     from puffer_phc_b200 import synth
     if args.only == "amp":
         make_amp(common)
+        return
+    if args.only == "mpjpe":
+        make_mpjpe()
         return
     if args.only == "loader":
         make_loader(ml, SkeletonTree, args.ref)
@@ -351,6 +367,7 @@ def main():
     save("sample_time.npz", samp)
     make_amp(common)
     make_loader(ml, SkeletonTree, args.ref)
+    make_mpjpe()
 
 
 if __name__ == "__main__":

@@ -429,3 +429,48 @@ def test_amp_observations_vs_golden(golden_amp):
         assert_close(npy(got), A[f"amp_{name}"], what=f"amp obs {name}", row_scale=True)
     d = common.dof_to_obs_smpl(cu(A["dof_pos"])[:, A["subset"]])
     assert_close(npy(d), A["amp_default"][:, 13:13 + 114], what="dof_to_obs_smpl", row_scale=True)
+
+
+def test_mpjpe_vs_golden(golden):
+    """compute_mpjpe (evaluation metric, humanoid_phc.py:159-163) on the strided PhysX view against the reference's outputs."""
+    from conftest import load_npz
+    from puffer_phc_b200.envs import common
+    M = load_npz("mpjpe.npz")
+    for sn in ("cmu_step", "synth_step"):
+        S = golden[sn]
+        st = cu(S["in_body_state"])
+        got = common.compute_mpjpe(st[:, :24, 0:3], cu(S["t0_rg_pos"]))        # non-contiguous view, consumed in place
+        assert_close(npy(got), M[sn], what=f"mpjpe {sn}")
+    assert common.compute_mpjpe(st[:0, :24, 0:3], cu(S["t0_rg_pos"])[:0]).shape == (0,)
+
+
+def test_step_host_pipelined_equals_device_step(golden):
+    """FusedStep.step_host (pinned host buffers, env ranges pipelined over copy / compute streams) returns exactly what the
+    device-resident step returns, for any chunk count, and accumulates the same RunningNorm moments."""
+    from puffer_phc_b200.fused_step import FusedStep, StepConfig
+    from puffer_phc_b200.policies.running_norm import RunningNorm
+    S = golden["synth_step"]
+    lib = make_lib(golden["synth_tables"])
+    N = S["in_progress"].shape[0]
+    keys = {"body_state": "in_body_state", "progress": "in_progress", "start_time": "in_start_time", "start_offset": "in_start_offset",
+            "motion_ids": "in_motion_ids", "global_offset": "in_global_offset", "dof_force": "in_dof_force", "dof_vel": "in_dof_vel"}
+    host = {k: torch.from_numpy(np.ascontiguousarray(S[v])).pin_memory() for k, v in keys.items()}
+    host["body_state"] = host["body_state"].reshape(N, -1)
+    dev = {k: v.to(DEV) for k, v in host.items()}
+    rms0 = RunningNorm(934).to(DEV)
+    fs0 = FusedStep(lib, N, StepConfig(), rms=rms0, normalize=True, accumulate_moments=True)
+    want = fs0(dev["body_state"], dev["progress"], dev["start_time"], dev["start_offset"], dev["motion_ids"], dev["global_offset"],
+               dev["dof_force"], dev["dof_vel"])
+    for chunks in (1, 3, 4, 1000):
+        rms = RunningNorm(934).to(DEV)
+        fs = FusedStep(lib, N, StepConfig(), rms=rms, normalize=True, accumulate_moments=True)
+        got = fs.step_host(host, chunks=chunks)
+        for k in ("reward", "reward_raw", "reset", "terminated"):
+            assert torch.equal(got[k], want[k].cpu()), (chunks, k)
+        assert torch.equal(fs.obs_buf, want["obs"]) and torch.equal(fs.obs_norm, want["obs_norm"]), chunks
+        m, m0 = npy(rms.moments_buffer()), npy(rms0.moments_buffer())
+        assert m[0] == m0[0] == N
+        np.testing.assert_allclose(m, m0, rtol=1e-13, atol=1e-12)
+    with pytest.raises(ValueError):
+        fs0(dev["body_state"], dev["progress"], dev["start_time"], dev["start_offset"], dev["motion_ids"], dev["global_offset"],
+            dev["dof_force"], dev["dof_vel"], env_range=(4, 16))

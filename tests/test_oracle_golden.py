@@ -150,3 +150,13 @@ def test_amp_observations(golden_amp):
         assert_close(got, want[:, : got.shape[1]], what=f"amp obs {name}", row_scale=True)
         if shp:      # pass-through columns
             assert_equal(want[:, got.shape[1]:], np.concatenate([A["shape"], A["limb"]], -1), "shape/limb columns")
+
+
+def test_mpjpe(golden):
+    """extras["mpjpe"] of the evaluation step (humanoid_phc.py:159-163) against the reference's torch expression."""
+    from conftest import load_npz
+    M = load_npz("mpjpe.npz")
+    for sn in ("cmu_step", "synth_step"):
+        S = golden[sn]
+        got = co.mpjpe(S["in_body_state"][:, :24, 0:3], S["t0_rg_pos"])
+        assert_close(got, M[sn], what=f"mpjpe {sn}")
