@@ -6,10 +6,11 @@
 One "step" = one pass of the hot path over one batch of N synthetic envs per GPU (BASELINE.json config 4/5:
 65536 envs per GPU over the 11313-clip AMASS-shaped synthetic library):
     phc_step_fused      2x motion-state (t, t+1) + imitation reward (+power) + reset + self obs + imitation obs
-                        + RunningNorm.forward output + fp64 column moments            (1 launch)
-    phc_rms_reduce_partials   folds the per-CTA moment partials                           (1 launch)
-    phc_gae             the amortised share of the advantage pass: N elements = N/32 envs x horizon 32  (1 launch)
-    every 32 steps (and at the last timed step): all-reduce of the moments (NCCL, N>1) + phc_rms_finalize.
+                        + RunningNorm.forward output + fp64 column moments added to per-CTA slots   (1 launch)
+    phc_gae             the amortised share of the advantage pass: N elements = N/32 envs x horizon 32  (1 launch, on a
+                        second stream: it is independent of the step and runs beside it)
+    every 32 steps (and at the last timed step): phc_rms_reduce_partials folds the per-CTA sums of the rollout, all-reduce of
+    the moments (NCCL, N>1) + phc_rms_finalize.
 Inputs are resident in HBM before the timed region; four input/output sets are rotated so that neither the
 sim state nor the observation buffers are L2-resident between iterations.  The e2e leg runs the same step
 through FusedStep.step_host with pinned HOST buffers (H2D of every per-env input, D2H of reward / flags).
@@ -219,7 +220,8 @@ def main():
     rms = RunningNorm(934).to(dev)
     # (PHC_BENCH_NORM / PHC_BENCH_MOM = 0 are tuning knobs only: they drop work from the step and mark the line invalid)
     knob_norm, knob_mom = os.environ.get("PHC_BENCH_NORM", "1") != "0", os.environ.get("PHC_BENCH_MOM", "1") != "0"
-    fs = FusedStep(lib, N, StepConfig(), rms=rms, normalize=knob_norm, accumulate_moments=knob_mom)
+    # defer_moments: the kernel adds every step's column sums to its per-CTA slots; they are folded once per rollout (flush_moments)
+    fs = FusedStep(lib, N, StepConfig(), rms=rms, normalize=knob_norm, accumulate_moments=knob_mom, defer_moments=True)
     ins, outs = [], []
     for s in range(SETS):
         S = synth.make_env_state(T, N, seed=1 + rank + 100 * s)
@@ -231,10 +233,12 @@ def main():
     adv = torch.empty(N * HORIZON, device=dev)
     # realistic normaliser state: one update from a first observation batch
     fs(*[ins[0][k] for k in ("body_state", "progress", "start_time", "start_offset", "motion_ids", "global_offset", "dof_force", "dof_vel")], out=outs[0])
+    fs.flush_moments()
     rms.finalize()
     torch.cuda.synchronize()
 
     stream = torch.cuda.current_stream()
+    gae_stream = torch.cuda.Stream(device=dev)       # the advantage pass is independent of the step: it runs beside it
     ev_a = [torch.cuda.Event(enable_timing=True) for _ in range(K)]
     ev_b = [torch.cuda.Event(enable_timing=True) for _ in range(K)]
     launches = {"n": 0}
@@ -245,21 +249,26 @@ def main():
             ev_a[timed_idx].record(stream)
         fs(S["body_state"], S["progress"], S["start_time"], S["start_offset"], S["motion_ids"], S["global_offset"], S["dof_force"], S["dof_vel"], out=O)
         if timed_idx is not None:
-            ev_b[timed_idx].record(stream)            # brackets phc_step_fused + the tiny partial reduce
+            ev_b[timed_idx].record(stream)            # brackets phc_step_fused
         lo = (i % HORIZON) * N
-        compute_gae_cuda(roll["dones"][lo:lo + N], roll["values"][lo:lo + N], roll["rewards"][lo:lo + N], 0.98, 0.2, out=adv[lo:lo + N])
-        launches["n"] += 3
+        with torch.cuda.stream(gae_stream):
+            compute_gae_cuda(roll["dones"][lo:lo + N], roll["values"][lo:lo + N], roll["rewards"][lo:lo + N], 0.98, 0.2, out=adv[lo:lo + N])
+        launches["n"] += 2
         if ((i + 1) % HORIZON == 0 or last) and knob_mom:
+            fs.flush_moments()                         # fold the per-CTA sums of the whole rollout (1 reduce + 1 memset)
             rms.finalize()                             # all-reduce of the fp64 moments (N>1) + running-average update
-            launches["n"] += 2                         # finalize + moments memset
+            launches["n"] += 2                         # phc_rms_reduce_partials + phc_rms_finalize (the two memsets are torch's)
+        if last:
+            stream.wait_stream(gae_stream)             # the timed region ends when both streams have drained
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
+    gae_stream.wait_stream(stream)
     for i in range(W):
-        one_step(i)
+        one_step(i, last=(i == W - 1))
     barrier()
     sampler = ClockSampler(local)
     if rank == 0:

@@ -285,6 +285,9 @@ typedef struct phc_step_out {
     uint8_t *terminated;         /* [N] _terminate_buf                                                     */
     double *moment_partials;     /* optional [phc_step_num_partials(), 2, 934] fp64: per-CTA sum and sum of
                                     squares of the raw obs columns; reduce with phc_rms_reduce_partials()  */
+    int accumulate_partials;     /* 0: the slots are overwritten with this step's sums; 1: this step's sums are ADDED to the
+                                    slots (CTA -> slot and env -> CTA are fixed, so the result is deterministic): zero the
+                                    buffer once, step a whole rollout, reduce once                         */
     float *ref_state_t;          /* optional debug [N,312]: blended reference pos72|rot96|vel72|ang72 at t */
     float *ref_state_t1;         /* optional debug [N,312] at t+1                                          */
 } phc_step_out;

@@ -67,7 +67,7 @@ class StepOut(C.Structure):
     _fields_ = [
         ("obs", C.c_void_p), ("obs_stride", C.c_int64), ("obs_norm", C.c_void_p), ("reward", C.c_void_p),
         ("reward_raw", C.c_void_p), ("raw_stride", C.c_int64), ("reset", C.c_void_p), ("terminated", C.c_void_p),
-        ("moment_partials", C.c_void_p), ("ref_state_t", C.c_void_p), ("ref_state_t1", C.c_void_p),
+        ("moment_partials", C.c_void_p), ("accumulate_partials", C.c_int), ("ref_state_t", C.c_void_p), ("ref_state_t1", C.c_void_p),
     ]
 
 

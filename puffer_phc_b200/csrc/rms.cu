@@ -85,58 +85,42 @@ __global__ void __launch_bounds__(RMS_THREADS) rms_moments_kernel(const float* _
     p[C + c] = q;
 }
 
-// Streaming variant for even C <= 2048 with 8-byte aligned rows: a block owns a contiguous range of rows and sweeps them
-// front to back (purely sequential DRAM traffic), thread = up to 4 column pairs (float2 loads), two rows in flight.
-constexpr int RMS_MAXPAIRS = 4;
-__global__ void __launch_bounds__(RMS_THREADS) rms_moments_rows_kernel(const float* __restrict__ x, int64_t xs, int64_t B, int C,
-                                                                       int64_t rows_per_block, double* __restrict__ partial) {
+// Streaming variant for even C with 8-byte aligned rows: a block owns a contiguous range of rows and sweeps them front to
+// back (purely sequential DRAM traffic).  thread = ONE column pair (float2 loads; the block is as wide as the row, rounded
+// up to a warp, so every thread carries the same work), RMS_ROWS rows in flight per thread before any arithmetic --
+// ~64 B per thread x ~1900 resident threads per SM keeps well over the ~45 KB per SM that HBM3e needs in flight.
+// Rows are added in order into one accumulator per column, so the result does not depend on RMS_ROWS.
+constexpr int RMS_ROWS = 8;
+constexpr int RMS_PAIR_THREADS_MAX = 512;
+__global__ void __launch_bounds__(RMS_PAIR_THREADS_MAX) rms_moments_rows_kernel(const float* __restrict__ x, int64_t xs, int64_t B, int C,
+                                                                                int64_t rows_per_block, double* __restrict__ partial) {
+    const int cp = blockIdx.y * blockDim.x + threadIdx.x;
+    if (cp >= (C >> 1)) return;
     const int64_t r0 = (int64_t)blockIdx.x * rows_per_block;
     const int64_t r1 = (r0 + rows_per_block < B) ? r0 + rows_per_block : B;
-    const int npairs = C >> 1;
-    double s[RMS_MAXPAIRS][2], q[RMS_MAXPAIRS][2];
-#pragma unroll
-    for (int u = 0; u < RMS_MAXPAIRS; ++u) { s[u][0] = s[u][1] = q[u][0] = q[u][1] = 0.0; }
+    double s0 = 0.0, s1 = 0.0, q0 = 0.0, q1 = 0.0;
+    const float2* col = reinterpret_cast<const float2*>(x) + cp;        // row r is at col + r * (xs / 2)
+    const int64_t xs2 = xs >> 1;
     int64_t r = r0;
-    for (; r + 2 <= r1; r += 2) {
-        float2 a[RMS_MAXPAIRS], b[RMS_MAXPAIRS];
+    for (; r + RMS_ROWS <= r1; r += RMS_ROWS) {
+        float2 a[RMS_ROWS];
 #pragma unroll
-        for (int u = 0; u < RMS_MAXPAIRS; ++u) {
-            const int cp = threadIdx.x + u * RMS_THREADS;
-            if (cp < npairs) {
-                a[u] = __ldg(reinterpret_cast<const float2*>(x + r * xs) + cp);
-                b[u] = __ldg(reinterpret_cast<const float2*>(x + (r + 1) * xs) + cp);
-            }
-        }
+        for (int k = 0; k < RMS_ROWS; ++k) a[k] = __ldcs(col + (r + k) * xs2);     // streamed once: evict-first
 #pragma unroll
-        for (int u = 0; u < RMS_MAXPAIRS; ++u) {
-            const int cp = threadIdx.x + u * RMS_THREADS;
-            if (cp < npairs) {
-                double d;
-                d = a[u].x; s[u][0] += d; q[u][0] = fma(d, d, q[u][0]);
-                d = a[u].y; s[u][1] += d; q[u][1] = fma(d, d, q[u][1]);
-                d = b[u].x; s[u][0] += d; q[u][0] = fma(d, d, q[u][0]);
-                d = b[u].y; s[u][1] += d; q[u][1] = fma(d, d, q[u][1]);
-            }
+        for (int k = 0; k < RMS_ROWS; ++k) {
+            const double d0 = a[k].x, d1 = a[k].y;
+            s0 += d0; q0 = fma(d0, d0, q0);
+            s1 += d1; q1 = fma(d1, d1, q1);
         }
     }
     for (; r < r1; ++r) {
-#pragma unroll
-        for (int u = 0; u < RMS_MAXPAIRS; ++u) {
-            const int cp = threadIdx.x + u * RMS_THREADS;
-            if (cp < npairs) {
-                const float2 a = __ldg(reinterpret_cast<const float2*>(x + r * xs) + cp);
-                double d;
-                d = a.x; s[u][0] += d; q[u][0] = fma(d, d, q[u][0]);
-                d = a.y; s[u][1] += d; q[u][1] = fma(d, d, q[u][1]);
-            }
-        }
+        const float2 a = __ldcs(col + r * xs2);
+        const double d0 = a.x, d1 = a.y;
+        s0 += d0; q0 = fma(d0, d0, q0);
+        s1 += d1; q1 = fma(d1, d1, q1);
     }
     double* p = partial + (int64_t)blockIdx.x * 2 * C;
-#pragma unroll
-    for (int u = 0; u < RMS_MAXPAIRS; ++u) {
-        const int cp = threadIdx.x + u * RMS_THREADS;
-        if (cp < npairs) { p[2 * cp] = s[u][0]; p[2 * cp + 1] = s[u][1]; p[C + 2 * cp] = q[u][0]; p[C + 2 * cp + 1] = q[u][1]; }
-    }
+    p[2 * cp] = s0; p[2 * cp + 1] = s1; p[C + 2 * cp] = q0; p[C + 2 * cp + 1] = q1;
 }
 
 // moments[1 + i] += sum_p partial[p][i] for i in [0, 2C); moments[0] += rows.  Deterministic: a block owns 32
@@ -234,8 +218,16 @@ extern "C" int phc_rms_moments(const float* x, int64_t x_stride, int64_t B, int 
     if (row_blocks > moments_row_blocks()) row_blocks = moments_row_blocks();
     const int64_t rows_per_block = (B + row_blocks - 1) / row_blocks;
     row_blocks = (B + rows_per_block - 1) / rows_per_block;
-    if ((C & 1) == 0 && C <= 2 * RMS_MAXPAIRS * RMS_THREADS && (x_stride & 1) == 0 && aligned8(x)) {
-        rms_moments_rows_kernel<<<(unsigned)row_blocks, RMS_THREADS, 0, s>>>(x, x_stride, B, C, rows_per_block, scratch);
+    if ((C & 1) == 0 && (x_stride & 1) == 0 && aligned8(x)) {
+        const int npairs = C >> 1;
+        int threads = ((npairs + 31) / 32) * 32;                  // as wide as the row ...
+        int chunks = 1;
+        if (threads > RMS_PAIR_THREADS_MAX) {                     // ... or the row split into equal column chunks
+            chunks = (npairs + RMS_PAIR_THREADS_MAX - 1) / RMS_PAIR_THREADS_MAX;
+            threads = (((npairs + chunks - 1) / chunks + 31) / 32) * 32;
+        }
+        dim3 grid((unsigned)row_blocks, (unsigned)chunks);
+        rms_moments_rows_kernel<<<grid, threads, 0, s>>>(x, x_stride, B, C, rows_per_block, scratch);
     } else {
         dim3 grid((unsigned)row_blocks, (unsigned)((C + RMS_THREADS - 1) / RMS_THREADS));
         rms_moments_kernel<<<grid, RMS_THREADS, 0, s>>>(x, x_stride, B, C, rows_per_block, scratch);

@@ -461,7 +461,12 @@ __global__ void __maxnreg__(ST_MAXREG) step_fused_kernel(const StepArgs a) {   /
 #pragma unroll
             for (int u = 0; u < ST_WPAIRS; ++u) {
                 const int c = 2 * (wtid + u * ST_WTHREADS);
-                if (c < OBS_W) { p[c] = msum[u][0]; p[c + 1] = msum[u][1]; p[OBS_W + c] = msq[u][0]; p[OBS_W + c + 1] = msq[u][1]; }
+                if (c < OBS_W) {
+                    if (out.accumulate_partials) {       // this CTA owns its slot: read-modify-write, deterministic
+                        msum[u][0] += p[c]; msum[u][1] += p[c + 1]; msq[u][0] += p[OBS_W + c]; msq[u][1] += p[OBS_W + c + 1];
+                    }
+                    p[c] = msum[u][0]; p[c + 1] = msum[u][1]; p[OBS_W + c] = msq[u][0]; p[OBS_W + c + 1] = msq[u][1];
+                }
             }
         }
     } else {

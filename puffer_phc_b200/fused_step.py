@@ -53,7 +53,11 @@ class StepConfig:
 class FusedStep:
     def __init__(self, motion_lib: MotionLibBase, num_envs: int, cfg: Optional[StepConfig] = None,
                  rms: Optional[RunningNorm] = None, normalize: bool = False, accumulate_moments: bool = False,
-                 debug_ref: bool = False):
+                 debug_ref: bool = False, defer_moments: bool = False):
+        """``accumulate_moments``: the kernel also produces the fp64 column sums ``RunningNorm.update`` needs.  By default they
+        are folded into ``rms``' pending moments after every step (one tiny reduce launch).  ``defer_moments=True`` lets the
+        kernel ADD every step's sums to its per-CTA slots instead; call ``flush_moments()`` once per rollout (before
+        ``rms.finalize()``) -- no per-step reduce launch at all."""
         self.lib = _ffi.load()
         self.motion_lib = motion_lib
         self.cfg = cfg or StepConfig()
@@ -63,6 +67,8 @@ class FusedStep:
         self.rms = rms
         self.normalize = bool(normalize)
         self.accumulate_moments = bool(accumulate_moments)
+        self.defer_moments = bool(defer_moments) and self.accumulate_moments
+        self._pending_rows = 0
         if (normalize or accumulate_moments) and rms is None:
             raise ValueError("normalize / accumulate_moments need a RunningNorm")
         c = self.cfg
@@ -144,17 +150,28 @@ class FusedStep:
         sout = _ffi.StepOut(
             obs.data_ptr(), obs.stride(0), obs_norm.data_ptr() if self.normalize else None, rew.data_ptr(), raw.data_ptr(),
             raw.stride(0), reset.data_ptr(), term.data_ptr(), self.partials.data_ptr() if self.accumulate_moments else None,
+            1 if self.defer_moments else 0,
             self.ref_t[row0:].data_ptr() if self.ref_t is not None else None,
             self.ref_t1[row0:].data_ptr() if self.ref_t1 is not None else None)
         with torch.cuda.device(self.device):
             _ffi.check(self.lib.phc_step_fused(C.byref(self.motion_lib.ctables), C.byref(sin), C.byref(self._ccfg), C.byref(sout),
                                                _ffi.stream_ptr()), "phc_step_fused")
-            if self.accumulate_moments:
+            if self.defer_moments:
+                self._pending_rows += N
+            elif self.accumulate_moments:
                 self.rms.accumulate_partials(self.partials, N)
         res = {"obs": obs, "reward": rew, "reward_raw": raw, "reset": reset, "terminated": term}
         if self.normalize:
             res["obs_norm"] = obs_norm
         return res
+
+    def flush_moments(self) -> None:
+        """``defer_moments`` mode: fold the sums the kernel has accumulated since the last flush into ``rms``' pending moments."""
+        if self.defer_moments and self._pending_rows:
+            with torch.cuda.device(self.device):
+                self.rms.accumulate_partials(self.partials, self._pending_rows)
+                self.partials.zero_()
+            self._pending_rows = 0
 
     # ---- host-buffer entry (end-to-end path): H2D of the per-env inputs, the kernel, D2H of reward / flags ------------
     _HOST_KEYS = ("body_state", "progress", "start_time", "start_offset", "motion_ids", "global_offset", "dof_force", "dof_vel")

@@ -474,3 +474,32 @@ def test_step_host_pipelined_equals_device_step(golden):
     with pytest.raises(ValueError):
         fs0(dev["body_state"], dev["progress"], dev["start_time"], dev["start_offset"], dev["motion_ids"], dev["global_offset"],
             dev["dof_force"], dev["dof_vel"], env_range=(4, 16))
+
+
+def test_deferred_moments_equal_per_step_moments(golden):
+    """defer_moments: the kernel adds each step's column sums to its per-CTA slots; one flush per rollout gives the same
+    pending moments as folding after every step."""
+    from puffer_phc_b200.fused_step import FusedStep, StepConfig
+    from puffer_phc_b200.policies.running_norm import RunningNorm
+    lib = make_lib(golden["synth_tables"])
+    S = golden["synth_step"]
+    args = [cu(S[k]) for k in ("in_body_state", "in_progress", "in_start_time", "in_start_offset", "in_motion_ids", "in_global_offset",
+                               "in_dof_force", "in_dof_vel")]
+    N = args[1].shape[0]
+    ra, rb = RunningNorm(934).to(DEV), RunningNorm(934).to(DEV)
+    fa = FusedStep(lib, N, StepConfig(), rms=ra, normalize=True, accumulate_moments=True)
+    fb = FusedStep(lib, N, StepConfig(), rms=rb, normalize=True, accumulate_moments=True, defer_moments=True)
+    for step in range(3):
+        args[1] = args[1] + 1                      # progress_buf advances: different observations every step
+        oa, ob = fa(*args), fb(*args)
+        assert torch.equal(oa["obs"], ob["obs"]) and torch.equal(oa["obs_norm"], ob["obs_norm"])
+    assert float(rb.moments_buffer().abs().sum()) == 0.0          # nothing folded yet
+    fb.flush_moments()
+    ma, mb = npy(ra.moments_buffer()), npy(rb.moments_buffer())
+    assert ma[0] == mb[0] == 3 * N
+    np.testing.assert_allclose(mb, ma, rtol=1e-13, atol=1e-10)
+    fb.flush_moments()                                            # idempotent when nothing is pending
+    np.testing.assert_allclose(npy(rb.moments_buffer()), mb, rtol=0, atol=0)
+    ra.finalize(); rb.finalize()
+    assert_close(npy(rb.running_mean), npy(ra.running_mean), rtol=1e-7, atol=1e-9, what="running_mean")
+    assert_close(npy(rb.running_var), npy(ra.running_var), rtol=1e-7, atol=1e-12, what="running_var")

@@ -52,7 +52,7 @@ def _run(harness, T, S, term, mask, use_mean, power):
     rw = 5 if power else 4
     obs, rew, raw = np.zeros((N, 934), np.float32), np.zeros(N, np.float32), np.zeros((N, rw), np.float32)
     rs, tm = np.zeros(N, np.uint8), np.zeros(N, np.uint8)
-    sout = _ffi.StepOut(_p(obs), 934, None, _p(rew), _p(raw), rw, _p(rs), _p(tm), None, None, None)
+    sout = _ffi.StepOut(_p(obs), 934, None, _p(rew), _p(raw), rw, _p(rs), _p(tm), None, 0, None, None)
     assert harness.harness_step(C.byref(mt), C.byref(sin), C.byref(cfg), C.byref(sout)) == 0
     return obs, rew, raw, rs.astype(bool), tm.astype(bool)
 
