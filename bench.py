@@ -220,6 +220,7 @@ def main():
     rms = RunningNorm(934).to(dev)
     # (PHC_BENCH_NORM / PHC_BENCH_MOM = 0 are tuning knobs only: they drop work from the step and mark the line invalid)
     knob_norm, knob_mom = os.environ.get("PHC_BENCH_NORM", "1") != "0", os.environ.get("PHC_BENCH_MOM", "1") != "0"
+    knob_gae_side = os.environ.get("PHC_BENCH_GAE_SIDE", "1") != "0"       # valid either way: where the GAE launch is queued
     # defer_moments: the kernel adds every step's column sums to its per-CTA slots; they are folded once per rollout (flush_moments)
     fs = FusedStep(lib, N, StepConfig(), rms=rms, normalize=knob_norm, accumulate_moments=knob_mom, defer_moments=True)
     ins, outs = [], []
@@ -251,7 +252,7 @@ def main():
         if timed_idx is not None:
             ev_b[timed_idx].record(stream)            # brackets phc_step_fused
         lo = (i % HORIZON) * N
-        with torch.cuda.stream(gae_stream):
+        with torch.cuda.stream(gae_stream if knob_gae_side else stream):
             compute_gae_cuda(roll["dones"][lo:lo + N], roll["values"][lo:lo + N], roll["rewards"][lo:lo + N], 0.98, 0.2, out=adv[lo:lo + N])
         launches["n"] += 2
         if ((i + 1) % HORIZON == 0 or last) and knob_mom:

@@ -35,36 +35,33 @@ __global__ void __launch_bounds__(GAE_THREADS) gae_blocked_kernel(const float* _
     float* s_v = s_d + pspan;
     float* s_r = s_v + pspan;
     float* s_a = s_r + pspan;                          // [padc<GAE_CH>(GAE_TILE)+1]
-    // persistent over tiles: the grid is one resident wave (no partially filled second wave at rollout sizes)
-    for (int64_t tile0 = (int64_t)blockIdx.x * GAE_TILE; tile0 < L; tile0 += (int64_t)gridDim.x * GAE_TILE) {
-        const int64_t avail = (L - tile0 < span) ? (L - tile0) : span;
-        for (int i = threadIdx.x; i < avail; i += GAE_THREADS) {
-            const int p = padc<GAE_CH>(i);
-            s_d[p] = __ldg(dones + tile0 + i);
-            s_v[p] = __ldg(values + tile0 + i);
-            s_r[p] = __ldg(rewards + tile0 + i);
-        }
-        __syncthreads();
-        const int c0 = threadIdx.x * GAE_CH;               // chunk [c0, c0+GAE_CH) relative to the tile
-        if (tile0 + c0 < L) {
-            // highest t_cur this thread evaluates: warm-up start, clipped to L-2 (adv[L-1] = 0 starts the true scan)
-            int64_t hi = tile0 + c0 + GAE_CH - 1 + K;
-            if (hi > L - 2) hi = L - 2;
-            float last = 0.0f;
-            for (int i = (int)(hi - tile0); i >= c0; --i) {
-                const int pn = padc<GAE_CH>(i + 1), pc = padc<GAE_CH>(i);
-                const float nnt = 1.0f - s_d[pn];
-                const float delta = (s_r[pn] + (gamma * s_v[pn]) * nnt) - s_v[pc];
-                last = delta + (gl * nnt) * last;
-                if (i < c0 + GAE_CH) s_a[pc] = last;
-            }
-            if (tile0 + c0 + GAE_CH > L - 1 && tile0 + c0 <= L - 1) s_a[padc<GAE_CH>((int)(L - 1 - tile0))] = 0.0f;
-        }
-        __syncthreads();
-        const int64_t nout = (L - tile0 < GAE_TILE) ? (L - tile0) : GAE_TILE;
-        for (int i = threadIdx.x; i < nout; i += GAE_THREADS) adv[tile0 + i] = s_a[padc<GAE_CH>(i)];
-        __syncthreads();                                   // the staging arrays are reused by the next tile
+    const int64_t tile0 = (int64_t)blockIdx.x * GAE_TILE;
+    const int64_t avail = (L - tile0 < span) ? (L - tile0) : span;
+    for (int i = threadIdx.x; i < avail; i += GAE_THREADS) {
+        const int p = padc<GAE_CH>(i);
+        s_d[p] = __ldg(dones + tile0 + i);
+        s_v[p] = __ldg(values + tile0 + i);
+        s_r[p] = __ldg(rewards + tile0 + i);
     }
+    __syncthreads();
+    const int c0 = threadIdx.x * GAE_CH;               // chunk [c0, c0+32) relative to the tile
+    if (tile0 + c0 < L) {
+        // highest t_cur this thread evaluates: warm-up start, clipped to L-2 (adv[L-1] = 0 starts the true scan)
+        int64_t hi = tile0 + c0 + GAE_CH - 1 + K;
+        if (hi > L - 2) hi = L - 2;
+        float last = 0.0f;
+        for (int i = (int)(hi - tile0); i >= c0; --i) {
+            const int pn = padc<GAE_CH>(i + 1), pc = padc<GAE_CH>(i);
+            const float nnt = 1.0f - s_d[pn];
+            const float delta = (s_r[pn] + (gamma * s_v[pn]) * nnt) - s_v[pc];
+            last = delta + (gl * nnt) * last;
+            if (i < c0 + GAE_CH) s_a[pc] = last;
+        }
+        if (tile0 + c0 + GAE_CH > L - 1 && tile0 + c0 <= L - 1) s_a[padc<GAE_CH>((int)(L - 1 - tile0))] = 0.0f;
+    }
+    __syncthreads();
+    const int64_t nout = (L - tile0 < GAE_TILE) ? (L - tile0) : GAE_TILE;
+    for (int i = threadIdx.x; i < nout; i += GAE_THREADS) adv[tile0 + i] = s_a[padc<GAE_CH>(i)];
 }
 
 // one warp: coalesced staging of 1024-element chunks, lane 0 runs the recurrence.
@@ -130,13 +127,7 @@ extern "C" int phc_gae(const float* dones, const float* values, const float* rew
     const int tile = ch * GAE_THREADS;
     const int span = tile + K + 1;
     const size_t smem = (size_t)(3 * ((span + span / ch) + 1) + (tile + tile / ch) + 1) * sizeof(float);
-    int64_t tiles = (L + tile - 1) / tile;
-    {   // one resident wave: CTAs per SM from the shared-memory footprint (64-thread CTAs: at most 32 per SM)
-        int64_t per_sm = (int64_t)(200 * 1024) / (int64_t)(smem + 1024);
-        per_sm = per_sm < 1 ? 1 : (per_sm > 32 ? 32 : per_sm);
-        const int64_t wave = per_sm * sm_count();
-        if (tiles > wave) tiles = wave;
-    }
+    const int64_t tiles = (L + tile - 1) / tile;
     if (ch == 8) {
         gae_blocked_kernel<8><<<(unsigned)tiles, GAE_THREADS, smem, s>>>(dones, values, rewards, L, gamma, gl, K, advantages);
     } else {
