@@ -204,11 +204,16 @@ class FusedStep:
         main = torch.cuda.current_stream(self.device)
         self._h2d_stream.wait_stream(main)              # earlier kernels may still read the staging buffers
         self._d2h_stream.wait_stream(main)
+        small = [k for k in keys if host[k].numel() * host[k].element_size() < (4 << 20)]     # per-env scalars: one copy each,
+        with torch.cuda.stream(self._h2d_stream):                                               # not one per range
+            for k in small:
+                d[k].copy_(host[k], non_blocking=True)
         for lo in range(0, N, per):
             hi = min(lo + per, N)
             with torch.cuda.stream(self._h2d_stream):
                 for k in keys:
-                    d[k][lo:hi].copy_(host[k][lo:hi], non_blocking=True)
+                    if k not in small:
+                        d[k][lo:hi].copy_(host[k][lo:hi], non_blocking=True)
             main.wait_stream(self._h2d_stream)
             out = self(d["body_state"], d["progress"], d["start_time"], d["start_offset"], d["motion_ids"], d["global_offset"],
                        d.get("dof_force"), d.get("dof_vel"), env_range=(lo, hi))
