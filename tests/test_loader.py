@@ -326,3 +326,52 @@ def test_load_data_filters_and_sorts(g):
     assert lib._num_unique_motions == 4 and len(lib._motion_data_list) == 4
     with pytest.raises(ValueError):
         lib.load_motions(skeleton_trees=[SimpleNamespace(node_names=["a"] * 23)], gender_betas=torch.zeros(1, 17), limb_weights=np.zeros((1, 10)))
+
+
+@pytest.mark.gpu
+def test_full_size_library_properties(g):
+    """BASELINE scale (11313 clips, ~2.5 M frames): size-independent properties of the table build, plus the oracle on a
+    sample of clips spread over the library."""
+    from puffer_phc_b200 import synth
+    from puffer_phc_b200.motion_file import RawClips
+    T = synth.make_motion_library(11313, seed=0, device=DEV)
+    nf = T["num_frames"].cpu().numpy()
+    fps = np.round(1.0 / T["motion_dt"].cpu().numpy()).astype(np.int32)
+    raw = RawClips.from_device([f"c{i}" for i in range(len(nf))], nf, fps, T["gts"][:, 0].double().contiguous(),
+                               T["motion_aa"].double().contiguous(), T["grs"].double().contiguous())
+    del T
+    lib = _lib(raw, max_length=300)
+    n = len(nf)
+    sk = _skeleton(g)
+    lib.load_motions(skeleton_trees=[sk] * n, gender_betas=torch.zeros(n, 17), limb_weights=np.zeros((n, 10)), random_sample=False)
+    d = raw.to_device(DEV)
+    F = int(nf.sum())
+    assert lib.gts.shape == (F, 24, 3) and lib.packed.shape == (F, 312)
+    assert torch.equal(lib.length_starts.cpu(), torch.from_numpy(np.concatenate([[0], np.cumsum(nf)[:-1]])))
+    # the root keeps float32(root translation), global rotations are the float32 cast of the input
+    assert torch.equal(lib.gts[:, 0], d["root_trans"].float())
+    assert torch.equal(lib.grs, d["pose_quat_global"].float())
+    # local rotations are unit quaternions with w >= 0 (quat_normalize) except the root, which keeps the input
+    assert float((lib.lrs[:, 1:].norm(dim=-1) - 1).abs().max()) < 1e-6 and float(lib.lrs[:, 1:, 3].min()) >= 0.0
+    # bone lengths are preserved by the forward kinematics
+    par = torch.from_numpy(g["parents"][1:]).to(DEV)
+    bone = (lib.gts[:, 1:] - lib.gts[:, par]).norm(dim=-1)
+    want = torch.from_numpy(np.linalg.norm(g["local_translation"][1:], axis=-1)).to(DEV)
+    assert float((bone - want).abs().max()) < 1e-5
+    # the last frame of every clip repeats the dof velocity of the one before it; the packed records mirror the tables
+    last = torch.from_numpy(np.cumsum(nf) - 1).to(DEV)
+    assert torch.equal(lib.dvs[last], lib.dvs[last - 1])
+    for k, (lo, hi) in {"gts": (0, 72), "grs": (72, 168), "gvs": (168, 240), "gavs": (240, 312)}.items():
+        assert torch.equal(lib.packed[:, lo:hi], getattr(lib, k).reshape(F, -1)), k
+    assert all(bool(torch.isfinite(getattr(lib, k)).all()) for k in FIELDS)
+    assert torch.equal(lib.grvs, lib.gvs[:, 0]) and torch.equal(lib.gravs, lib.gavs[:, 0])
+    # oracle on every 400th clip
+    starts = lib.length_starts.cpu().numpy()
+    for i in range(0, n, 400):
+        c, a, m = raw.clip(i), int(starts[i]), int(nf[i])
+        o = co.build_clip(c["pose_quat_global"].cpu().numpy(), c["root_trans_offset"].cpu().numpy(), g["parents"], g["local_translation"], c["fps"])
+        for k in BITS:
+            assert_equal(_bits(getattr(lib, k)[a:a + m].cpu().numpy()), _bits(o[k]), f"clip {i} {k} bits")
+        for k in ("gvs", "gavs"):
+            assert_close(getattr(lib, k)[a:a + m].cpu().numpy(), o[k], rtol=1e-6, atol=1e-7, what=f"clip {i} {k}")
+        assert_close(lib.dvs[a:a + m].cpu().numpy(), o["dvs"], rtol=1e-5, atol=1e-6, what=f"clip {i} dvs")
