@@ -59,6 +59,8 @@ def srcline(k):
     return ''
 print('--- top by samples')
 for k,n in samp.most_common(25): print(f'{100*n/ts:5.1f}%  {per[k]/N:7.1f}/env  {k}  {srcline(k)}')
+print('--- top by executed warp instructions')
+for k,n in per.most_common(40): print(f'{n/N:8.1f}/unit  {100*samp[k]/ts:5.1f}% of samples  {k}  {srcline(k)}')
 print('--- top sass by samples')
 top=sorted(data,key=lambda r:-int(r[isamp]))[:25]
 for r in top: 

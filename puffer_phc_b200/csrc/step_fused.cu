@@ -8,8 +8,8 @@
 // Design (persistent, warp-specialised, one CTA per SM):
 //   * compute groups: each iteration the CTA owns S consecutive envs.  A group of THREE warps works on FOUR envs
 //     (4 x 24 bodies = 96 lanes: every lane carries one body, no idle lanes) and there are two groups per four envs:
-//         role A: reference at t   -> reward terms, termination test, power term, self observation (pos / rot)
-//         role B: reference at t+1 -> imitation (task) observation, self observation (vel / ang-vel)
+//         role A: reference at t   -> reward terms, termination test, power term and their per-env reductions / exponentials
+//         role B: reference at t+1 -> imitation (task) observation and the whole self observation (the only heading-frame math)
 //     Every (env, role) owns a private shared-memory buffer (PhysX record | frame 0 | frame 1 | dof force/vel).  The
 //     NEXT env's record and frames are fetched with cp.async right after the current ones have been read into
 //     registers, so the gathers fly behind ~700 instructions of math and never occupy registers (without this the
@@ -67,11 +67,30 @@ constexpr int ST_WWARPS = ST_WRITERS;                // writer warps
 #endif
 constexpr int ST_WTHREADS = ST_WWARPS * 32;
 constexpr int ST_THREADS = (ST_CWARPS + ST_WWARPS + 1) * 32;     // + the planner warp
-constexpr int ST_PLANS = 4;                          // plan ring: plans are produced three iterations ahead
+constexpr int ST_PLANS = 4;                          // plan ring: plans are produced three iterations ahead (a ring of 8 with its own
+                                                     // "free" barriers, seven ahead, measured slower: 0.186 vs 0.176 ms)
 constexpr int ST_WPAIRS = (OBS_W / 2 + ST_WTHREADS - 1) / ST_WTHREADS;  // column pairs owned by a writer thread
 constexpr int ST_DOF_F = 144;                        // dof_force (69, padded to 72) | dof_vel (69, padded to 72)
 constexpr int ST_WBUF_F = 3 * FRAME_F + ST_DOF_F;    // per compute warp: sim record | frame 0 | frame 1 | dof force/vel
 constexpr unsigned SPIN_LIMIT = 1u << 22;            // a stuck mbarrier traps (after a few seconds) instead of hanging the GPU
+
+// -DST_PROFILE=1: lane 0 of every compute warp accumulates the clock cycles it spends in each wait of its loop
+// (0 cp.async landing + group barrier, 1 plan barrier, 2 tile-release barrier, 3 group barriers: buffers free + the two of the
+// reduction, 4 whole loop) into
+// g_prof[SM][warp][5]; read with phc_debug_profile().  Tuning builds only.
+#ifndef ST_PROFILE
+#define ST_PROFILE 0
+#endif
+#if ST_PROFILE
+__device__ unsigned long long g_prof[160][32][5];
+#define PROF_DECL unsigned long long prof_t[5] = {0, 0, 0, 0, 0}; long long prof_c = 0, prof_l = clock64();
+#define PROF_BEGIN prof_c = clock64();
+#define PROF_END(k) prof_t[k] += (unsigned long long)(clock64() - prof_c);
+#else
+#define PROF_DECL
+#define PROF_BEGIN
+#define PROF_END(k)
+#endif
 
 struct StepArgs {
     phc_motion_tables t;
@@ -275,6 +294,7 @@ __global__ void __maxnreg__(ST_MAXREG) step_fused_kernel(const StepArgs a) {   /
         }
         cp_async_commit();
         int it = 0;
+        PROF_DECL
         for (int64_t blk = blockIdx.x; blk < a.num_blocks; blk += gridDim.x, ++it) {
             const int64_t e = blk * ST_ENVS + slot;
             const bool valid = e < in.N;
@@ -282,8 +302,10 @@ __global__ void __maxnreg__(ST_MAXREG) step_fused_kernel(const StepArgs a) {   /
             float* my_tile = tiles + (b * ST_ENVS + slot) * OBS_W;
 
             // ---- operands of this body: shared memory -> registers, blend the two frames ----------------
+            PROF_BEGIN
             cp_async_wait_all();
             group_sync(bar_id);                                                // the copies of all 96 lanes have landed
+            PROF_END(0)
             BodyState body{}, ref{};
             V3 root_p{};
             Q4 root_q{0.0f, 0.0f, 0.0f, 1.0f};
@@ -301,26 +323,29 @@ __global__ void __maxnreg__(ST_MAXREG) step_fused_kernel(const StepArgs a) {   /
                     power = (fabsf(df[0] * df[72]) + fabsf(df[1] * df[73])) + fabsf(df[2] * df[74]);
                 }
             }
+            PROF_BEGIN
             group_sync(bar_id);                                                // everyone has read: the buffers are free again
+            PROF_END(3)
             // ---- fetch the next env's record and frames behind the math -----------------------------------
             EnvPlan nxt{};
             {
                 const int64_t nblk = blk + gridDim.x;
                 if (nblk < a.num_blocks) {
                     const int d = (it + 1) % ST_PLANS;
+                    PROF_BEGIN
                     mbar_wait<ST_CHINT>(&pfull[d], ((it + 1) / ST_PLANS) & 1);
+                    PROF_END(1)
                     nxt = plans[d * ST_NBUF + buf];
                     if (nxt.valid) issue_env<PACKED>(a, nxt, nblk * ST_ENVS + slot, role, wbuf, j);
                 }
                 cp_async_commit();
             }
+            PROF_BEGIN
             if (use >= 1) mbar_wait<ST_CHINT>(&empty[b], (use - 1) & 1);               // tile buffer b released by the writers
+            PROF_END(2)
 
-            float hz = 0.0f, hw = 1.0f;
-            if (valid) heading_quat_direct(root_q, hz, hw);                    // upright start: no base-rot removal
-            const ZRot hrot = zrot_make(hz, hw);
             if (role == 0) {
-                // ============ role A: reward, reset, power, self observation (reference at t) ============
+                // ============ role A: reward, reset, power (reference at t) ============
                 float* rj = red + (slot * NB + j) * 8;
                 if (valid) {
                     float sp, sr, sv, sa, dist = 0.0f;
@@ -332,11 +357,10 @@ __global__ void __maxnreg__(ST_MAXREG) step_fused_kernel(const StepArgs a) {   /
                     *reinterpret_cast<float4*>(rj) = make_float4(sp, sr, sv, sa);
                     *reinterpret_cast<float2*>(rj + 4) = make_float2(dist, power);
                     if (DEBUG_REF && out.ref_state_t) store_ref(out.ref_state_t + e * FRAME_F, j, ref);
-                    float* o = my_tile;
-                    if (j == 0) o[0] = root_p.z;                                          // common.py:40
-                    self_obs_pos_rot_fma(body, root_p, hz, hw, hrot, j, o + 1 + 3 * (j - 1), o + 70 + 6 * j);   // vel / ang blocks: role B
                 }
+                PROF_BEGIN
                 group_sync(bar_id);
+                PROF_END(3)
                 {   // second stage: lane (value v, part p) of the env adds bodies 6p .. 6p+5, in order
                     const int v = j >> 2, p4 = j & 3;
                     const float* src = red + (slot * NB + 6 * p4) * 8 + v;
@@ -345,30 +369,42 @@ __global__ void __maxnreg__(ST_MAXREG) step_fused_kernel(const StepArgs a) {   /
                     for (int k = 1; k < 6; ++k) s = s + src[8 * k];
                     red2[(slot * 6 + v) * 4 + p4] = s;
                 }
+                PROF_BEGIN
                 group_sync(bar_id);
-                if (valid && j == 0) {      // one leader lane per env: fixed-order totals and the env-level tail
-                    float tot[6];
-#pragma unroll
-                    for (int v = 0; v < 6; ++v) {
-                        const float4 q4 = *reinterpret_cast<const float4*>(red2 + (slot * 6 + v) * 4);
-                        tot[v] = ((q4.x + q4.y) + q4.z) + q4.w;
+                PROF_END(3)
+                // env-level tail.  The six lanes j < 6 of an env sit in ONE warp (the env's 24 lanes start at lane 0, 24, 16 or 8 of a
+                // warp): lane v totals value v in the fixed order and, for the four reward terms, evaluates its exponential kernel
+                // (common.py:300-316) -- four expf side by side instead of one after the other in a single leader lane; the leader
+                // (j == 0) collects them with shuffles.
+                float val = 0.0f;
+                if (j < 6) {
+                    const float4 q4 = *reinterpret_cast<const float4*>(red2 + (slot * 6 + j) * 4);
+                    val = ((q4.x + q4.y) + q4.z) + q4.w;
+                    if (j < 4) {
+                        const float inv = (j == 1) ? (1.0f / (float)NB) : (1.0f / (3.0f * (float)NB));
+                        val = expf(-cfg.k[j] * (val * inv));
                     }
+                }
+                const int base = lane - j;                                                // lane of this env's j == 0 (same warp for j < 6)
+                const float r0 = __shfl_sync(FULL, val, base & 31), r1 = __shfl_sync(FULL, val, (base + 1) & 31);
+                const float r2 = __shfl_sync(FULL, val, (base + 2) & 31), r3 = __shfl_sync(FULL, val, (base + 3) & 31);
+                const float t4 = __shfl_sync(FULL, val, (base + 4) & 31), t5 = __shfl_sync(FULL, val, (base + 5) & 31);
+                if (valid && j == 0) {
                     bool fallen = false;
                     if (cfg.enable_early_termination) {
                         if (cfg.use_mean) {                                               // common.py:342-346
                             const int first = __ffs(cfg.reset_body_mask) - 1;
-                            fallen = (tot[4] / (float)__popc(cfg.reset_body_mask & 0xffffffu)) > __ldg(in.term_dist + first);
+                            fallen = (t4 / (float)__popc(cfg.reset_body_mask & 0xffffffu)) > __ldg(in.term_dist + first);
                         } else {
-                            fallen = tot[4] > 0.0f;
+                            fallen = t4 > 0.0f;
                         }
                         fallen = fallen && (cur.prog > 1);                                // common.py:354
                     }
-                    float raw[4];
-                    float rew = reward_from_sq_sums(tot[0], tot[1], tot[2], tot[3], (float)NB, cfg.k, cfg.w, raw);
+                    float rew = ((cfg.w[0] * r0 + cfg.w[1] * r1) + cfg.w[2] * r2) + cfg.w[3] * r3;    // common.py:318-320
                     float* rr = out.reward_raw + e * out.raw_stride;
-                    rr[0] = raw[0]; rr[1] = raw[1]; rr[2] = raw[2]; rr[3] = raw[3];
+                    rr[0] = r0; rr[1] = r1; rr[2] = r2; rr[3] = r3;
                     if (in.dof_force) {
-                        float pr = -cfg.power_coef * tot[5];
+                        float pr = -cfg.power_coef * t5;
                         if (cur.prog <= 3) pr = 0.0f;
                         rew = rew + pr;
                         rr[4] = pr;
@@ -378,8 +414,13 @@ __global__ void __maxnreg__(ST_MAXREG) step_fused_kernel(const StepArgs a) {   /
                     out.reset[e] = (cur.t >= cur.mlen) ? 1 : (fallen ? 1 : 0);            // humanoid_phc.py:1315, common.py:362
                 }
             } else if (valid) {
-                // ============ role B: imitation observation (reference at t+1) + self vel / ang-vel ===========
+                // ============ role B: every observation block (task obs against the reference at t+1, self obs) ===========
+                float hz, hw;
+                heading_quat_direct(root_q, hz, hw);                           // upright start: no base-rot removal; role A needs no heading
+                const ZRot hrot = zrot_make(hz, hw);
                 if (DEBUG_REF && out.ref_state_t1) store_ref(out.ref_state_t1 + e * FRAME_F, j, ref);
+                if (j == 0) my_tile[0] = root_p.z;                                        // common.py:40
+                self_obs_pos_rot_fma(body, root_p, hz, hw, hrot, j, my_tile + 1 + 3 * (j - 1), my_tile + 70 + 6 * j);
                 self_obs_vel_ang_fma(body, hrot, my_tile + 214 + 3 * j, my_tile + 286 + 3 * j);
                 float* q = my_tile + OBS_SELF;
                 task_obs_body_fma(body, ref, root_p, hz, hw, hrot, q + 3 * j, q + 72 + 6 * j, q + 216 + 3 * j, q + 288 + 3 * j,
@@ -390,6 +431,10 @@ __global__ void __maxnreg__(ST_MAXREG) step_fused_kernel(const StepArgs a) {   /
             if (lane == 0) mbar_arrive(&full[b]);
             cur = nxt;
         }
+#if ST_PROFILE
+        prof_t[4] = (unsigned long long)(clock64() - prof_l);
+        if (lane == 0) for (int k = 0; k < 5; ++k) g_prof[blockIdx.x][warp][k] = prof_t[k];
+#endif
         cp_async_wait_all();
     } else if (warp < ST_CWARPS + ST_WWARPS) {
         // ====================================== writer warps =======================================
@@ -571,3 +616,9 @@ extern "C" int phc_step_fused(const phc_motion_tables* t, const phc_step_in* in,
     else step_fused_kernel<false, true><<<grid, ST_THREADS, ST_SMEM, s>>>(a);
     return check_launch(fn);
 }
+
+#if ST_PROFILE
+extern "C" int phc_debug_profile(unsigned long long* out_h /* [160*32*5] host */) {
+    return (int)cudaMemcpyFromSymbol(out_h, phc::g_prof, sizeof(phc::g_prof));
+}
+#endif
