@@ -190,6 +190,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-other-configs", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     rank = int(os.environ.get("RANK", "0"))
@@ -316,6 +317,55 @@ def main():
                "note": "H2D: PhysX record + per-env scalars + dof force/vel from pinned memory; D2H: reward, reward_raw, reset, "
                        "terminated (what the reference moves to the host each step, clean_pufferl/structs.py:123-128); obs stays in HBM for the policy"}
 
+    # ---- the smaller BASELINE configs, reported beside the headline (rank 0, N=1 only; not the bench line) ---------------
+    other = None
+    if world == 1 and not args.no_other_configs:
+        other = {}
+        n2 = 4096                                                            # config 2: 4096 envs, fused obs/reward/reset kernel
+        rms2 = RunningNorm(934).to(dev)
+        fs2 = FusedStep(lib, n2, StepConfig(), rms=rms2, normalize=True, accumulate_moments=True, defer_moments=True)
+        S2 = [synth.make_env_state(T, n2, seed=11 + s) for s in range(SETS)]
+        keys = ("body_state", "progress", "start_time", "start_offset", "motion_ids", "global_offset", "dof_force", "dof_vel")
+        graphs = [fs2.capture(*[S2[s][k] for k in keys])[0] for s in range(SETS)]      # one CUDA graph per input set
+        for i in range(20):
+            graphs[i % SETS].replay()
+        torch.cuda.synchronize()
+        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        K2 = 2000
+        a0.record(stream)
+        for i in range(K2):
+            graphs[i % SETS].replay()
+        a1.record(stream)
+        torch.cuda.synchronize()
+        us = a0.elapsed_time(a1) / K2 * 1e3
+        other["config2_4096_envs_fused_step"] = {
+            "us_per_step": us, "env_steps_per_s": n2 / (us * 1e-6), "gbs": STEP_BYTES * n2 / (us * 1e-6) / 1e9,
+            "note": "phc_step_fused replayed from a CUDA graph (launch-latency-bound: 59 MB of traffic, ~4 block iterations per SM)"}
+        R3 = synth.make_rollout(4096, HORIZON, seed=2, device=dev)              # config 3: c_gae 4096 x 32, gamma 0.98, lambda 0.2
+        adv3 = torch.empty(4096 * HORIZON, device=dev)
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(stream)
+        with torch.cuda.stream(side):
+            for _ in range(3):
+                compute_gae_cuda(R3["dones"], R3["values"], R3["rewards"], 0.98, 0.2, out=adv3)
+        stream.wait_stream(side)
+        torch.cuda.synchronize()
+        g3 = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g3):
+            compute_gae_cuda(R3["dones"], R3["values"], R3["rewards"], 0.98, 0.2, out=adv3)
+        for _ in range(20):
+            g3.replay()
+        torch.cuda.synchronize()
+        a0.record(stream)
+        for _ in range(K2):
+            g3.replay()
+        a1.record(stream)
+        torch.cuda.synchronize()
+        us3 = a0.elapsed_time(a1) / K2 * 1e3
+        other["config3_gae_4096x32"] = {"us_per_call": us3, "elements": 4096 * HORIZON,
+                                        "gbs": GAE_BYTES_PER_ELEM * 4096 * HORIZON / (us3 * 1e-6) / 1e9,
+                                        "note": "phc_gae replayed from a CUDA graph (2 MB of traffic: launch-latency-bound)"}
+
     if rank == 0:
         peak, peak_src = measured_peak_gbs()
         achieved = STEP_BYTES * N / (kern_ms * 1e-3) / 1e9
@@ -334,6 +384,8 @@ def main():
             line["invalid"] = "tuning run: PHC_BENCH_NORM/PHC_BENCH_MOM dropped work from the step"
         if e2e:
             line["e2e"] = e2e
+        if other:
+            line["other_configs"] = other
         if world == 1 and not args.no_cpu_baseline:
             threads = os.cpu_count() or 1
             host_tables = {k: v.cpu() for k, v in T.items()}

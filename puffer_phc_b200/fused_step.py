@@ -165,6 +165,12 @@ class FusedStep:
             res["obs_norm"] = obs_norm
         return res
 
+    def count_replayed(self, steps: int = 1) -> None:
+        """``defer_moments`` with CUDA-graph replay: a replay runs the kernel (which adds its sums to the slots) but not the Python
+        bookkeeping, so tell the object how many steps were replayed before ``flush_moments()``."""
+        if self.defer_moments:
+            self._pending_rows += int(steps) * self.N
+
     def flush_moments(self) -> None:
         """``defer_moments`` mode: fold the sums the kernel has accumulated since the last flush into ``rms``' pending moments."""
         if self.defer_moments and self._pending_rows:
