@@ -95,11 +95,14 @@ __device__ __forceinline__ double filter_at(const T* col, int C, int lo, int nf,
     return tmp;
 }
 
+// JT = 24: the SMPL humanoid, every row stride / tap offset is a compile-time constant (the index arithmetic otherwise rivals
+// the floating-point work); JT = 0: J read from the arguments.
+template <int JT>
 __global__ void __launch_bounds__(BT_THREADS, 3) build_tables_kernel(const __grid_constant__ BuildArgs A) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const phc_build_in& in = A.in;
     const phc_build_out& o = A.out;
-    const int J = in.J, C = 3 * J;
+    const int J = JT ? JT : in.J, C = 3 * J;
     const int QS = 4 * J + 4;        // quaternion row stride (floats): lane = frame float4 accesses are bank-conflict free
     const int PS = C + 1;            // position row stride (floats): odd, lane = frame scalar accesses are conflict free
     double* sW = reinterpret_cast<double*>(smem_raw);                    // [BT_VROWS][C]  raw angular velocity (float64)
@@ -386,10 +389,12 @@ extern "C" int phc_build_motion_tables(const phc_build_in* in, const phc_build_o
     }
     const size_t smem = build_smem_bytes(in->J);
     {   // per device; cheap enough to repeat on every call of a load-time function
-        cudaError_t e = cudaFuncSetAttribute(build_tables_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)build_smem_bytes(32));
+        cudaError_t e = cudaFuncSetAttribute(build_tables_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)build_smem_bytes(32));
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(build_tables_kernel<NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)build_smem_bytes(NB));
         if (e != cudaSuccess) return fail((int)e, "phc_build_motion_tables: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
     }
-    build_tables_kernel<<<(unsigned)in->n_tiles, BT_THREADS, smem, (cudaStream_t)stream>>>(args);
+    if (in->J == NB) build_tables_kernel<NB><<<(unsigned)in->n_tiles, BT_THREADS, smem, (cudaStream_t)stream>>>(args);
+    else build_tables_kernel<0><<<(unsigned)in->n_tiles, BT_THREADS, smem, (cudaStream_t)stream>>>(args);
     return check_launch("phc_build_motion_tables");
 }
 
