@@ -143,12 +143,19 @@ def run_reference(args, rank, world):
     R = synth.make_rollout(sample // HORIZON, HORIZON, seed=2)
     d, v, r = (R[k].numpy() for k in ("dones", "values", "rewards"))
     mean, var = torch.zeros(1, 934), torch.ones(1, 934)
+    gae_fn, gae_kind = (lambda: c_oracle.gae(d, v, r, 0.98, 0.2)), "C c_gae restatement"
+    try:                                     # the reference's OWN c_gae.pyx, compiled into oracle/_ref/ by build() where the reference exists
+        sys.path.insert(0, os.path.join(ROOT, "oracle", "_ref"))
+        import c_gae as ref_c_gae
+        gae_fn, gae_kind = (lambda: ref_c_gae.compute_gae(d, v, r, 0.98, 0.2)), "the reference's own c_gae.pyx (oracle/_ref)"
+    except Exception:
+        pass
     times = []
     for i in range(args.warmup + args.steps):
         t0 = time.perf_counter()
         out = tp.step(T, S)
         tp.rms_forward(out["obs"], mean, var)
-        c_oracle.gae(d, v, r, 0.98, 0.2)
+        gae_fn()
         if i >= args.warmup:
             times.append(time.perf_counter() - t0)
     total = sum(times)
@@ -160,7 +167,7 @@ def run_reference(args, rank, world):
         "config": workload_config(args.envs, world, sample_note=f"each step = a bounded sample of {sample} envs of the workload"),
         "cpu_baseline": {"value": value, "unit": "env-steps/s", "cores": threads, "kind": "port",
                          "sample": f"{sample} envs x {len(times)} steps, torch {torch.__version__} eager CPU port of the reference "
-                                   "functions (oracle/torch_port.py) + C c_gae restatement"},
+                                   f"functions (oracle/torch_port.py) + {gae_kind}"},
         "e2e": {"value": value, "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
