@@ -186,6 +186,12 @@ int phc_reset_ref_state(const phc_motion_tables *t, const int64_t *env_ids, cons
                         float *root_states, float *dof_pos, float *dof_vel, float *body_state, int64_t env_stride,
                         phc_stream_t stream);
 
+/* MotionLibBase._calc_frame_blend(time, len, num_frames, dt) (puffer_phc/motion_lib.py:655-665), elementwise over n entries:
+ * phase = clip(time/len, 0, 1); time < 0 -> 0; idx0 = int64(phase * (nf-1)); idx1 = min(idx0+1, nf-1);
+ * blend = clip((time - idx0*dt)/dt, 0, 1).  Integer outputs are bit-exact against torch. */
+int phc_frame_blend(const float *time, const float *len, const int64_t *num_frames, const float *dt, int64_t n,
+                    int64_t *frame_idx0, int64_t *frame_idx1, float *blend, phc_stream_t stream);
+
 /* MotionLibBase.sample_time_interval arithmetic (puffer_phc/motion_lib.py:526-535); the uniform
  * phase stays on the caller's torch generator.  out = float(int64((phase*len)/(1/30))) * (1/30).
  * div_mode 0: IEEE division (torch CPU); 1: multiply by fp32 reciprocal (torch CUDA divides a

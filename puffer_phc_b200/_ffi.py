@@ -20,7 +20,7 @@ EXPORTS = (
     "phc_version", "phc_last_error", "phc_pack_frames", "phc_motion_state", "phc_reset_ref_state", "phc_sample_time_interval",
     "phc_imitation_obs_v6", "phc_self_obs_smpl_max", "phc_amp_obs_smpl", "phc_imitation_reward", "phc_im_reset",
     "phc_step_num_partials", "phc_step_fused", "phc_rms_forward", "phc_rms_scratch_doubles", "phc_rms_moments",
-    "phc_rms_reduce_partials", "phc_rms_finalize", "phc_gae", "phc_build_motion_tables", "phc_build_motion_aa", "phc_cast_f64_f32", "phc_mpjpe",
+    "phc_rms_reduce_partials", "phc_rms_finalize", "phc_gae", "phc_build_motion_tables", "phc_build_motion_aa", "phc_cast_f64_f32", "phc_mpjpe", "phc_frame_blend",
 )
 
 PHC_OK, PHC_EINVAL, PHC_EALIGN, PHC_ESHAPE, PHC_EUNSUPPORTED = 0, -1, -2, -3, -4
@@ -110,6 +110,7 @@ def _declare(lib):
     lib.phc_build_motion_aa.argtypes = [P, I, P, P, I64, I64, P, P, P, P, P]
     lib.phc_cast_f64_f32.argtypes = [P, I64, P, P]
     lib.phc_mpjpe.argtypes = [View, View, I64, I, P, P]
+    lib.phc_frame_blend.argtypes = [P, P, P, P, I64, P, P, P, P]
     for name in EXPORTS:
         fn = getattr(lib, name)
         if fn.restype is C.c_int and name not in ("phc_version", "phc_step_num_partials"):

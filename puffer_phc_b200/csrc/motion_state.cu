@@ -229,6 +229,27 @@ extern "C" int phc_sample_time_interval(const float* phase, const float* motion_
     return check_launch("phc_sample_time_interval");
 }
 
+// MotionLibBase._calc_frame_blend on its own (motion_lib.py:655-665): thread = element.
+__global__ void frame_blend_kernel(const float* __restrict__ time, const float* __restrict__ len, const int64_t* __restrict__ nf,
+                                   const float* __restrict__ dt, int64_t n, int64_t* __restrict__ i0, int64_t* __restrict__ i1,
+                                   float* __restrict__ blend) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    int64_t a, b;
+    float bl;
+    phc::frame_blend(__ldg(time + i), __ldg(len + i), __ldg(nf + i), __ldg(dt + i), a, b, bl);
+    i0[i] = a; i1[i] = b; blend[i] = bl;
+}
+
+extern "C" int phc_frame_blend(const float* time, const float* len, const int64_t* num_frames, const float* dt, int64_t n,
+                               int64_t* frame_idx0, int64_t* frame_idx1, float* blend, phc_stream_t stream) {
+    PHC_REQUIRE(n >= 0, PHC_EINVAL, "phc_frame_blend: n < 0");
+    if (n == 0) return PHC_OK;
+    PHC_REQUIRE(time && len && num_frames && dt && frame_idx0 && frame_idx1 && blend, PHC_EINVAL, "phc_frame_blend: NULL pointer");
+    frame_blend_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(time, len, num_frames, dt, n, frame_idx0, frame_idx1, blend);
+    return check_launch("phc_frame_blend");
+}
+
 extern "C" int phc_pack_frames(const phc_motion_tables* t, float* packed, phc_stream_t stream) {
     PHC_REQUIRE(t && packed, PHC_EINVAL, "phc_pack_frames: NULL pointer");
     PHC_REQUIRE(t->gts && t->grs && t->gvs && t->gavs, PHC_EINVAL, "phc_pack_frames: gts/grs/gvs/gavs required");

@@ -389,8 +389,57 @@ class MotionLibBase:
         return self.get_motion_state(motion_ids, motion_times, offset=None, keys=("root_pos",))
 
     def _calc_frame_blend(self, time, len, num_frames, dt):   # noqa: A002  (reference signature, motion_lib.py:655-665)
-        """Reference-signature helper; evaluated by the same kernel through a one-motion-per-row table view."""
-        raise NotImplementedError("use get_motion_state(..., debug=True) to obtain frame_idx0/frame_idx1/blend")
+        """-> ``(frame_idx0, frame_idx1, blend)`` for per-element ``time``, motion ``len``, ``num_frames`` and frame ``dt``."""
+        _ffi.require_cuda(time, len, num_frames, dt)
+        n = time.numel()
+        t, ln, dtt = (x.to(torch.float32).contiguous().view(-1) for x in (time, len, dt))
+        nf = num_frames.to(torch.int64).contiguous().view(-1)
+        if not (ln.numel() == n and nf.numel() == n and dtt.numel() == n):
+            raise ValueError("_calc_frame_blend: time, len, num_frames and dt must have the same number of elements")
+        i0 = torch.empty(n, dtype=torch.int64, device=time.device)
+        i1 = torch.empty(n, dtype=torch.int64, device=time.device)
+        bl = torch.empty(n, dtype=torch.float32, device=time.device)
+        with torch.cuda.device(time.device):
+            _ffi.check(self._lib.phc_frame_blend(_ffi.ptr(t), _ffi.ptr(ln), _ffi.ptr(nf), _ffi.ptr(dtt), n, _ffi.ptr(i0), _ffi.ptr(i1),
+                                                 _ffi.ptr(bl), _ffi.stream_ptr()), "_calc_frame_blend")
+        return i0.view(time.shape), i1.view(time.shape), bl.view(time.shape)
+
+    def _get_num_bodies(self):                                # motion_lib.py:667-668
+        return self.num_bodies
+
+    # ---- sampling weights (PMCP hard-negative mining; motion_lib.py:454-508).  Plain bookkeeping on _sampling_prob ------------
+    def _key_indexes(self, failed_keys):
+        all_keys = self._motion_data_keys.tolist()
+        return [all_keys.index(k) for k in failed_keys]
+
+    def _uniform_sampling(self):
+        self._sampling_prob = torch.ones(self._num_unique_motions).to(self._device) / self._num_unique_motions
+
+    def update_hard_sampling_weight(self, failed_keys):
+        """Train only on the failed sequences (uniform over them); uniform over everything when none failed."""
+        if len(failed_keys) > 0:
+            idx = self._key_indexes(failed_keys)
+            self._sampling_prob[:] = 0
+            self._sampling_prob[idx] = 1 / len(idx)
+            print(f"Auto PMCP: training on only {len(failed_keys)} seqs")
+        else:
+            self._uniform_sampling()
+
+    def update_soft_sampling_weight(self, failed_keys):
+        """Train mostly on the failed sequences: their termination count goes up and the sampling probability follows it."""
+        if len(failed_keys) > 0:
+            self._termination_history[self._key_indexes(failed_keys)] += 1
+            self.update_sampling_prob(self._termination_history)
+            print(f"Auto PMCP: training mostly on {len(self._sampling_prob.nonzero())} seqs")
+        else:
+            self._uniform_sampling()
+
+    def update_sampling_prob(self, termination_history):
+        if len(termination_history) == len(self._termination_history) and termination_history.sum() > 0:
+            self._sampling_prob[:] = termination_history / termination_history.sum()
+            self._termination_history = termination_history
+            return True
+        return False
 
 
 class MotionLibSMPL(MotionLibBase):

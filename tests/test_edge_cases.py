@@ -89,3 +89,48 @@ def test_nan_sim_state_does_not_terminate_or_crash(lib):
     keep[5] = False
     for k in ("obs", "reward", "reward_raw", "reset", "terminated"):
         assert torch.equal(out[k][keep], clean[k][keep]), k
+
+
+def test_calc_frame_blend_entry_point_bit_exact(lib):
+    """MotionLibBase._calc_frame_blend (row A1) with the reference's signature, against the reference's own outputs."""
+    T, S = load_npz("synth_tables.npz"), load_npz("synth_step.npz")
+    ids = S["in_motion_ids"]
+    for tag in ("t0", "t1"):
+        i0, i1, bl = lib._calc_frame_blend(cu(S[tag]), cu(T["motion_len"][ids]), cu(T["num_frames"][ids]), cu(T["motion_dt"][ids]))
+        assert i0.dtype == torch.int64 and i1.dtype == torch.int64 and bl.dtype == torch.float32
+        assert_equal(i0.cpu().numpy(), S[f"{tag}_idx0"], f"{tag} idx0")
+        assert_equal(i1.cpu().numpy(), S[f"{tag}_idx1"], f"{tag} idx1")
+        assert_equal(bl.cpu().numpy().view(np.uint32), S[f"{tag}_blend"].view(np.uint32), f"{tag} blend bits")
+    e = torch.zeros(0, device=DEV)
+    assert lib._calc_frame_blend(e, e, torch.zeros(0, dtype=torch.long, device=DEV), e)[0].shape == (0,)
+    with pytest.raises(ValueError):
+        lib._calc_frame_blend(torch.zeros(3, device=DEV), torch.zeros(2, device=DEV), torch.zeros(3, dtype=torch.long, device=DEV), torch.zeros(3, device=DEV))
+
+
+def test_sampling_weight_updates():
+    """update_hard / update_soft_sampling_weight / update_sampling_prob (motion_lib.py:454-508) drive load_motions' multinomial."""
+    from types import SimpleNamespace
+    from puffer_phc_b200.motion_file import RawClips
+    from puffer_phc_b200.motion_lib import MotionLibSMPL
+    g = load_npz("loader.npz")
+    raw = RawClips.from_dict({f"clip{i}": {"root_trans_offset": g[f"clip{i}_root_trans_offset"], "pose_aa": g[f"clip{i}_pose_aa"],
+                                          "pose_quat_global": g[f"clip{i}_pose_quat_global"], "beta": np.zeros(16), "fps": int(g[f"clip{i}_fps"])}
+                              for i in range(4)})
+    ml = MotionLibSMPL(SimpleNamespace(motion_file=raw, device=DEV, min_length=-1, max_length=50, im_eval=False, is_deterministic=False, step_dt=1 / 30))
+    assert ml._sampling_prob.tolist() == [0.25] * 4
+    ml.update_hard_sampling_weight(["clip1", "clip3"])
+    assert ml._sampling_prob.tolist() == [0.0, 0.5, 0.0, 0.5]
+    torch.manual_seed(0)
+    from puffer_phc_b200.skeleton import SkeletonTree
+    sk = SkeletonTree([f"b{j}" for j in range(24)], g["parents"].astype(np.int32), g["local_translation"])
+    ml.load_motions(skeleton_trees=[sk] * 16, gender_betas=torch.zeros(16, 17), limb_weights=np.zeros((16, 10)))     # random_sample=True
+    assert set(ml._curr_motion_ids.tolist()) <= {1, 3} and len(ml.curr_motion_keys) == 16
+    assert ml.sample_motions(8).max() < 16
+    ml.update_hard_sampling_weight([])
+    assert ml._sampling_prob.tolist() == [0.25] * 4
+    ml.update_soft_sampling_weight(["clip0"])
+    ml.update_soft_sampling_weight(["clip0", "clip2"])
+    assert ml._termination_history.tolist() == [2.0, 0.0, 1.0, 0.0]
+    assert_close(ml._sampling_prob.cpu().numpy(), np.array([2 / 3, 0, 1 / 3, 0], np.float32), rtol=1e-6, atol=0, what="soft prob")
+    assert ml.update_sampling_prob(torch.zeros(4, device=DEV)) is False and ml.update_sampling_prob(torch.ones(3, device=DEV)) is False
+    assert ml._get_num_bodies() == 24
