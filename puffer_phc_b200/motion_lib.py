@@ -168,8 +168,14 @@ class MotionLibBase:
             raise ValueError("load_motions: every clip needs at least 2 frames (np.gradient / the dof-velocity loop raise in the reference)")
 
         # ---- which clips get built -------------------------------------------------------------------
-        if dedupe and heading is None:
-            _, first, inverse = np.unique(np.stack([idx, crop], 1), axis=0, return_index=True, return_inverse=True)
+        same_tree = all(t is skeleton_trees[0] for t in skeleton_trees)
+        dedupe = dedupe and heading is None
+        if dedupe:
+            tree_no = np.zeros(n, dtype=np.int64)
+            if not same_tree:                       # slots only share rows when they also share the skeleton object
+                seen = {}
+                tree_no = np.array([seen.setdefault(id(t), len(seen)) for t in skeleton_trees], dtype=np.int64)
+            _, first, inverse = np.unique(np.stack([idx, crop, tree_no], 1), axis=0, return_index=True, return_inverse=True)
             inverse = inverse.reshape(-1)
         else:
             first, inverse = np.arange(n), np.arange(n)
@@ -180,7 +186,6 @@ class MotionLibBase:
         tiles = np.zeros(len(first) + 1, dtype=np.int64)
         np.cumsum((b_nf + _ffi.BUILD_TILE - 1) // _ffi.BUILD_TILE, out=tiles[1:])
         J = self.num_joints
-        same_tree = all(t is skeleton_trees[0] for t in skeleton_trees)
         if same_tree:
             lt = skeleton_trees[0].local_translation.to(torch.float32).reshape(1, J, 3)
         else:
@@ -216,7 +221,7 @@ class MotionLibBase:
         self.grvs, self.gravs = self.gvs[:, 0], self.gavs[:, 0]            # global_root_(angular_)velocity = body 0 (:408-409)
 
         # ---- _motion_aa: the reference appends each slot's UNCROPPED pose_aa (motion_lib.py:381) ----------
-        if dedupe and heading is None:      # one segment per built clip, aligned with the frame rows
+        if dedupe:                          # one segment per built clip, aligned with the frame rows
             seg_slot, seg_src, seg_len, c_lo = first, raw.starts[idx[first]] + crop[first], b_nf, np.zeros(len(first), np.int64)
         else:                               # one segment per slot: the whole clip, heading applied inside the crop window
             seg_slot, seg_src, seg_len, c_lo = np.arange(n), raw.starts[idx], seq_len, crop
@@ -241,11 +246,12 @@ class MotionLibBase:
         self._motion_fps = torch.tensor(fps, device=dev, dtype=torch.float32)
         self._motion_dt = torch.tensor(1.0 / fps, device=dev, dtype=torch.float32)
         self._motion_num_frames = torch.tensor(kept, device=dev)
-        gb = torch.as_tensor(gender_betas).to(torch.float32)
+        gb = torch.as_tensor(gender_betas).detach().cpu().to(torch.float32)
         bodies = gb.clone()
         bodies[torch.from_numpy(~has_beta)] = 0                                  # torch.zeros(17) without beta
         self._motion_bodies = bodies.to(dev)
-        self._motion_limb_weights = torch.tensor(np.array(limb_weights), device=dev, dtype=torch.float32)
+        lw = limb_weights.detach().cpu().numpy() if torch.is_tensor(limb_weights) else np.array(limb_weights)
+        self._motion_limb_weights = torch.tensor(lw, device=dev, dtype=torch.float32)
         self._num_motions = n
         self.length_starts = torch.from_numpy(b_out[:-1][inverse]).to(dev)      # :416-419 (shared rows when de-duplicated)
         self.motion_ids = torch.arange(n, dtype=torch.long, device=dev)

@@ -375,3 +375,27 @@ def test_full_size_library_properties(g):
         for k in ("gvs", "gavs"):
             assert_close(getattr(lib, k)[a:a + m].cpu().numpy(), o[k], rtol=1e-6, atol=1e-7, what=f"clip {i} {k}")
         assert_close(lib.dvs[a:a + m].cpu().numpy(), o["dvs"], rtol=1e-5, atol=1e-6, what=f"clip {i} dvs")
+
+
+@pytest.mark.gpu
+def test_dedupe_respects_per_slot_skeletons(g):
+    """Slots that load the same clip with DIFFERENT skeleton objects must not share rows; with dedupe they still answer queries
+    exactly like the un-deduplicated load."""
+    from puffer_phc_b200.skeleton import SkeletonTree
+    raw = _synthetic_raw([40, 52], seed=9, fps=(30,))
+    lib = _lib(raw, max_length=60)
+    mk = lambda s: SkeletonTree([f"b{j}" for j in range(24)], g["parents"].astype(np.int32), g["local_translation"] * s)   # noqa: E731
+    a, b = mk(1.0), mk(1.2)
+    sks = [a, b, a, b, a, a]
+    idx = torch.tensor([0, 0, 0, 1, 1, 1])
+    kw = dict(skeleton_trees=sks, gender_betas=torch.zeros(6, 17, device=DEV), limb_weights=torch.zeros(6, 10), sample_idxes=idx)
+    ids, times = torch.arange(6, device=DEV), torch.linspace(0.0, 1.2, 6, device=DEV)
+    lib.load_motions(**kw)
+    want = lib.get_motion_state(ids, times)
+    lib.load_motions(dedupe=True, **kw)
+    assert lib.gts.shape[0] == 40 + 40 + 52 + 52          # (clip 0, a), (clip 0, b), (clip 1, b), (clip 1, a)
+    got = lib.get_motion_state(ids, times)
+    for k in want:
+        if k != "motion_aa":
+            assert torch.equal(want[k], got[k]), k
+    assert not torch.equal(got["rg_pos"][0], got["rg_pos"][1])     # same clip and time, different skeleton
