@@ -55,6 +55,9 @@ static_assert(ST_ENVS % 4 == 0 && ST_NBUF <= 32, "a compute group handles 4 envs
 #ifndef ST_WRITERS
 #define ST_WRITERS 4
 #endif
+#ifndef ST_PLAN_EARLY
+#define ST_PLAN_EARLY 0                              // 1: the planner computes plan p before it waits for the ring slot -- no gain
+#endif                                               // (0.1745 vs 0.1729 ms): the plans are not what the critical role waits for
 #ifndef ST_PREFETCH
 #define ST_PREFETCH 0                                // 1: planner lanes prefetch the coming frame / sim records into L2 -- measured
                                                      // SLOWER (0.179 -> 0.220 ms): the prefetches queue ahead of the demand gathers
@@ -530,14 +533,22 @@ __global__ void __maxnreg__(ST_MAXREG) step_fused_kernel(const StepArgs a) {   /
         // without plan p, so the tile barrier polled here never runs a full phase ahead of this warp.
         int p = 0;
         for (int64_t blk = blockIdx.x; blk < a.num_blocks; blk += gridDim.x, ++p) {
+#if ST_PLAN_EARLY
+            // the plan is computed (its two dependent load latencies paid) BEFORE the wait for the ring slot
+            const int64_t e = blk * ST_ENVS + lane % ST_ENVS;
+            EnvPlan pl{};
+            if (lane < ST_NBUF) pl = make_plan(a, e, lane / ST_ENVS);
+#endif
             if (p >= ST_PLANS - 1) {
                 const int q = p - (ST_PLANS - 1);
                 mbar_wait<ST_WHINT>(&full[q % ST_TILES], (q / ST_TILES) & 1);
             }
             const int d = p % ST_PLANS;
             if (lane < ST_NBUF) {
+#if !ST_PLAN_EARLY
                 const int64_t e = blk * ST_ENVS + lane % ST_ENVS;
                 const EnvPlan pl = make_plan(a, e, lane / ST_ENVS);
+#endif
                 plans[d * ST_NBUF + lane] = pl;
 #if ST_PREFETCH
                 if (pl.valid) {
