@@ -17,8 +17,10 @@ PHC_HD BodyState blend_frames(const BodyState& a, const BodyState& b, float blen
     BodyState r;
     r.p = V3{lerp(a.p.x, b.p.x, om, blend) + off.x, lerp(a.p.y, b.p.y, om, blend) + off.y, lerp(a.p.z, b.p.z, om, blend) + off.z};
     r.q = slerp_rcp(a.q, b.q, blend);
-    r.v = V3{lerp(a.v.x, b.v.x, om, blend), lerp(a.v.y, b.v.y, om, blend), lerp(a.v.z, b.v.z, om, blend)};
-    r.w = V3{lerp(a.w.x, b.w.x, om, blend), lerp(a.w.y, b.w.y, om, blend), lerp(a.w.z, b.w.z, om, blend)};
+    // velocities feed fp32 outputs only (no index, no flag): one fused multiply-add per component, <= 1 ulp from the reference's
+    // (1-b)*x0 + b*x1; the position above keeps the reference's three roundings because the termination test reads it
+    r.v = V3{fmaf(blend, b.v.x, om * a.v.x), fmaf(blend, b.v.y, om * a.v.y), fmaf(blend, b.v.z, om * a.v.z)};
+    r.w = V3{fmaf(blend, b.w.x, om * a.w.x), fmaf(blend, b.w.y, om * a.w.y), fmaf(blend, b.w.z, om * a.w.z)};
     return r;
 }
 

@@ -209,8 +209,10 @@ PHC_HD float quat_angle(Q4 q) {
 // 2 acos w wrapped into (-pi, pi]; only its square is used, so the wrap is done in closed form instead of the
 // reference's atan2(sin, cos) round trip (equal to a few ulp; the round trip itself carries ~5e-7 of noise).
 PHC_HD float quat_angle_sq(Q4 q) {
-    float s = sqrtf(1.0f - q.w * q.w);
-    if (!(fabsf(s) > 1e-5f)) return 0.0f;
+    // the reference masks on |sqrt(1 - w^2)| > 1e-5; in fp32 1 - w^2 is either <= 0 / NaN or >= 2^-24, so the test is "> 0" and the
+    // square root (only ever used for this decision) is not needed: identical mask, shorter dependent chain
+    const float x = 1.0f - q.w * q.w;
+    if (!(x > 1e-10f)) return 0.0f;
     float a = 2.0f * acosf(q.w);
     if (a > 3.14159265358979323846f) a = a - 6.28318530717958647692f;
     return a * a;
