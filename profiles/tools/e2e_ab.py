@@ -23,11 +23,11 @@ a.record()
 for _ in range(10): dbig.copy_(big, non_blocking=True)
 b.record(); torch.cuda.synchronize()
 out["raw_h2d_gbs"] = big.numel() * 4 * 10 / (a.elapsed_time(b) * 1e-3) / 1e9
-for chunks in (1, 2, 4, 8):
-    for i in range(3): fs.step_host(hin[i % 2], chunks=chunks)
+for chunks, hs in ((1, 1), (2, 1), (4, 1), (2, 2), (4, 2), (4, 3), (8, 2)):
+    for i in range(3): fs.step_host(hin[i % 2], chunks=chunks, h2d_streams=hs)
     torch.cuda.synchronize()
     t0 = time.perf_counter()
-    for i in range(16): fs.step_host(hin[i % 2], chunks=chunks)
+    for i in range(16): fs.step_host(hin[i % 2], chunks=chunks, h2d_streams=hs)
     torch.cuda.synchronize()
-    out[f"chunks{chunks}_ms"] = (time.perf_counter() - t0) / 16 * 1e3
+    out[f"chunks{chunks}_h2d{hs}_ms"] = (time.perf_counter() - t0) / 16 * 1e3
 print(json.dumps(out))

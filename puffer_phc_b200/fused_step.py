@@ -182,7 +182,7 @@ class FusedStep:
     # ---- host-buffer entry (end-to-end path): H2D of the per-env inputs, the kernel, D2H of reward / flags ------------
     _HOST_KEYS = ("body_state", "progress", "start_time", "start_offset", "motion_ids", "global_offset", "dof_force", "dof_vel")
 
-    def step_host(self, host: Dict[str, torch.Tensor], chunks: int = 4) -> Dict[str, torch.Tensor]:
+    def step_host(self, host: Dict[str, torch.Tensor], chunks: int = 4, h2d_streams: int = 1) -> Dict[str, torch.Tensor]:
         """Same step with HOST (ideally pinned) input tensors, as a simulator living on the host would hand them over.
         Returns host tensors ``reward, reward_raw, reset, terminated`` (valid on return); the observation buffers stay on
         the device for the policy (``self.obs_buf`` / ``self.obs_norm``).
@@ -201,26 +201,31 @@ class FusedStep:
         for k in keys:
             if host[k].is_cuda:
                 raise RuntimeError("step_host expects host tensors; use __call__ for device-resident inputs")
-        if not hasattr(self, "_h2d_stream"):
-            self._h2d_stream, self._d2h_stream = torch.cuda.Stream(device=self.device), torch.cuda.Stream(device=self.device)
+        if not hasattr(self, "_h2d_streams") or len(self._h2d_streams) != max(1, int(h2d_streams)):
+            # several copy streams: the fixed set-up time of one DMA transfer hides under the payload of another
+            self._h2d_streams = [torch.cuda.Stream(device=self.device) for _ in range(max(1, int(h2d_streams)))]
+            self._d2h_stream = torch.cuda.Stream(device=self.device)
         d, N = self._dev_in, self.N
         chunks = max(1, min(int(chunks), N // 8)) if N >= 8 else 1
         per = -(-N // chunks)
         per += (-per) % 8
         main = torch.cuda.current_stream(self.device)
-        self._h2d_stream.wait_stream(main)              # earlier kernels may still read the staging buffers
+        hs = self._h2d_streams
+        for st in hs:
+            st.wait_stream(main)                        # earlier kernels may still read the staging buffers
         self._d2h_stream.wait_stream(main)
         small = [k for k in keys if host[k].numel() * host[k].element_size() < (4 << 20)]     # per-env scalars: one copy each,
-        with torch.cuda.stream(self._h2d_stream):                                               # not one per range
+        with torch.cuda.stream(hs[-1]):                                                         # not one per range
             for k in small:
                 d[k].copy_(host[k], non_blocking=True)
+        big = [k for k in keys if k not in small]
         for lo in range(0, N, per):
             hi = min(lo + per, N)
-            with torch.cuda.stream(self._h2d_stream):
-                for k in keys:
-                    if k not in small:
-                        d[k][lo:hi].copy_(host[k][lo:hi], non_blocking=True)
-            main.wait_stream(self._h2d_stream)
+            for i, k in enumerate(big):
+                with torch.cuda.stream(hs[i % len(hs)]):
+                    d[k][lo:hi].copy_(host[k][lo:hi], non_blocking=True)
+            for st in hs:
+                main.wait_stream(st)
             out = self(d["body_state"], d["progress"], d["start_time"], d["start_offset"], d["motion_ids"], d["global_offset"],
                        d.get("dof_force"), d.get("dof_vel"), env_range=(lo, hi))
             self._d2h_stream.wait_stream(main)
