@@ -55,6 +55,9 @@ static_assert(ST_ENVS % 4 == 0 && ST_NBUF <= 32, "a compute group handles 4 envs
 #ifndef ST_WRITERS
 #define ST_WRITERS 4
 #endif
+#ifndef ST_A_WAITS_TILE
+#define ST_A_WAITS_TILE 0
+#endif
 #ifndef ST_PLAN_EARLY
 #define ST_PLAN_EARLY 0                              // 1: the planner computes plan p before it waits for the ring slot -- no gain
 #endif                                               // (0.1745 vs 0.1729 ms): the plans are not what the critical role waits for
@@ -344,7 +347,9 @@ __global__ void __maxnreg__(ST_MAXREG) step_fused_kernel(const StepArgs a) {   /
                 cp_async_commit();
             }
             PROF_BEGIN
-            if (use >= 1) mbar_wait<ST_CHINT>(&empty[b], (use - 1) & 1);               // tile buffer b released by the writers
+            // tile buffer b released by the writers -- only role B writes tile rows; role A never waits for the writers (it cannot
+            // run more than two iterations ahead of role B anyway: its plans depend on full[] of both roles)
+            if ((ST_A_WAITS_TILE || role == 1) && use >= 1) mbar_wait<ST_CHINT>(&empty[b], (use - 1) & 1);
             PROF_END(2)
 
             if (role == 0) {
