@@ -55,6 +55,12 @@ static_assert(ST_ENVS % 4 == 0 && ST_NBUF <= 32, "a compute group handles 4 envs
 #ifndef ST_WRITERS
 #define ST_WRITERS 4
 #endif
+#ifndef ST_TMA_LOADS
+#define ST_TMA_LOADS 0                               // 1: sim record + packed frames arrive by TMA bulk loads (one lane issues three
+                                                     // cp.async.bulk with mbarrier byte counting instead of 12 cp.async per lane);
+                                                     // bit-identical, measured 0.1728-0.1742 vs 0.1716-0.1719 ms: the staging
+                                                     // instructions are not what the critical role waits for
+#endif
 #ifndef ST_A_WAITS_TILE
 #define ST_A_WAITS_TILE 0
 #endif
@@ -139,6 +145,16 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity) {
         if (!done && ++spins > SPIN_LIMIT) __trap();
     }
 }
+// TMA bulk LOAD global -> shared, completion counted in bytes on an mbarrier (one instruction per 16-byte aligned block instead
+// of 78 per-lane 16-byte cp.async for a 1248-byte record).
+__device__ __forceinline__ void bulk_load(void* smem_dst, const void* gsrc, unsigned bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(smem_dst)), "l"(gsrc), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void bulk_store(void* gdst, const void* smem_src, unsigned bytes) {
     asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(smem_u32(smem_src)), "r"(bytes) : "memory");
@@ -218,22 +234,40 @@ __device__ __forceinline__ void stage_frame(const phc_motion_tables& T, int64_t 
 }
 
 // Async fetch of everything the 24 lanes of (env e, role) read: PhysX record, two frames, (role A) dof force / vel.
+// BULK (packed frame records and 16-byte aligned sim rows): lane j == 0 announces the byte count on the buffer's mbarrier and
+// issues one TMA bulk load per record; the other lanes issue nothing for them.  Otherwise every lane stages its share with
+// cp.async (completion through cp.async groups + the group barrier).
 template <bool PACKED>
-__device__ __forceinline__ void issue_env(const StepArgs& a, const EnvPlan& p, int64_t e, int role, float* wbuf, int j) {
+__device__ __forceinline__ void issue_env(const StepArgs& a, const EnvPlan& p, int64_t e, int role, float* wbuf, int j, uint64_t* lbar) {
     const phc_step_in& in = a.in;
     const float* rec = in.body_state + e * in.env_stride;
-    if (a.sim_vec) {
+    const bool two = p.f1 != p.f0;
+    if (PACKED && ST_TMA_LOADS) {
+        if (j == 0) {
+            const unsigned fbytes = FRAME_F * 4;
+            mbar_expect_tx(lbar, (a.sim_vec ? (unsigned)SIM_F * 4 : 0u) + (two ? 2 * fbytes : fbytes));
+            if (a.sim_vec) bulk_load(wbuf, rec, SIM_F * 4, lbar);
+            bulk_load(wbuf + FRAME_F, a.t.packed + p.f0 * FRAME_F, fbytes, lbar);
+            if (two) bulk_load(wbuf + 2 * FRAME_F, a.t.packed + p.f1 * FRAME_F, fbytes, lbar);
+        }
+        if (!a.sim_vec) {
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            const int i = j + NB * k;
-            if (i < SIM_F / 4) cp_async16(wbuf + 4 * i, rec + 4 * i);
+            for (int k = 0; k < REC; ++k) cp_async4(wbuf + j + NB * k, rec + j + NB * k);
         }
     } else {
+        if (a.sim_vec) {
 #pragma unroll
-        for (int k = 0; k < REC; ++k) cp_async4(wbuf + j + NB * k, rec + j + NB * k);
+            for (int k = 0; k < 4; ++k) {
+                const int i = j + NB * k;
+                if (i < SIM_F / 4) cp_async16(wbuf + 4 * i, rec + 4 * i);
+            }
+        } else {
+#pragma unroll
+            for (int k = 0; k < REC; ++k) cp_async4(wbuf + j + NB * k, rec + j + NB * k);
+        }
+        stage_frame<PACKED>(a.t, p.f0, wbuf + FRAME_F, j);
+        if (two) stage_frame<PACKED>(a.t, p.f1, wbuf + 2 * FRAME_F, j);
     }
-    stage_frame<PACKED>(a.t, p.f0, wbuf + FRAME_F, j);
-    if (p.f1 != p.f0) stage_frame<PACKED>(a.t, p.f1, wbuf + 2 * FRAME_F, j);
     if (role == 0 && in.dof_force) {
 #pragma unroll
         for (int k = 0; k < 3; ++k) {
@@ -271,6 +305,7 @@ __global__ void __maxnreg__(ST_MAXREG) step_fused_kernel(const StepArgs a) {   /
     uint64_t* full = bars;                    // [ST_TILES] tile b written by all compute warps
     uint64_t* empty = bars + ST_TILES;        // [ST_TILES] tile b drained by the writers
     uint64_t* pfull = bars + 2 * ST_TILES;    // [ST_PLANS] plan set d written by the planning writer warp
+    uint64_t* lfull = pfull + ST_PLANS;       // [2S] staging buffer (role, slot): bytes of the TMA bulk loads have landed
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const phc_step_in& in = a.in;
@@ -280,6 +315,8 @@ __global__ void __maxnreg__(ST_MAXREG) step_fused_kernel(const StepArgs a) {   /
     if (tid == 0) {
         for (int i = 0; i < ST_TILES; ++i) { mbar_init(&full[i], ST_CWARPS); mbar_init(&empty[i], 1); }
         for (int i = 0; i < ST_PLANS; ++i) mbar_init(&pfull[i], 1);
+        for (int i = 0; i < ST_NBUF; ++i) mbar_init(&lfull[i], 1);
+        fence_mbar_init();
     }
     __syncthreads();
 
@@ -296,7 +333,7 @@ __global__ void __maxnreg__(ST_MAXREG) step_fused_kernel(const StepArgs a) {   /
         if ((int64_t)blockIdx.x < a.num_blocks) {
             mbar_wait<ST_CHINT>(&pfull[0], 0);
             cur = plans[buf];
-            if (cur.valid) issue_env<PACKED>(a, cur, (int64_t)blockIdx.x * ST_ENVS + slot, role, wbuf, j);
+            if (cur.valid) issue_env<PACKED>(a, cur, (int64_t)blockIdx.x * ST_ENVS + slot, role, wbuf, j, &lfull[buf]);
         }
         cp_async_commit();
         int it = 0;
@@ -310,7 +347,8 @@ __global__ void __maxnreg__(ST_MAXREG) step_fused_kernel(const StepArgs a) {   /
             // ---- operands of this body: shared memory -> registers, blend the two frames ----------------
             PROF_BEGIN
             cp_async_wait_all();
-            group_sync(bar_id);                                                // the copies of all 96 lanes have landed
+            if (PACKED && ST_TMA_LOADS && cur.valid) mbar_wait<ST_CHINT>(&lfull[buf], it & 1);   // the bulk loads of this env have landed
+            group_sync(bar_id);                                                // the cp.async copies of all 96 lanes have landed
             PROF_END(0)
             BodyState body{}, ref{};
             V3 root_p{};
@@ -342,7 +380,7 @@ __global__ void __maxnreg__(ST_MAXREG) step_fused_kernel(const StepArgs a) {   /
                     mbar_wait<ST_CHINT>(&pfull[d], ((it + 1) / ST_PLANS) & 1);
                     PROF_END(1)
                     nxt = plans[d * ST_NBUF + buf];
-                    if (nxt.valid) issue_env<PACKED>(a, nxt, nblk * ST_ENVS + slot, role, wbuf, j);
+                    if (nxt.valid) issue_env<PACKED>(a, nxt, nblk * ST_ENVS + slot, role, wbuf, j, &lfull[buf]);
                 }
                 cp_async_commit();
             }
@@ -573,7 +611,7 @@ __global__ void __maxnreg__(ST_MAXREG) step_fused_kernel(const StepArgs a) {   /
 
 constexpr size_t ST_SMEM = (size_t)(ST_TILES * ST_ENVS * OBS_W + ST_NBUF * ST_WBUF_F + ST_ENVS * NB * 8 + ST_ENVS * 24) * sizeof(float) +
                            ST_PLANS * ST_NBUF * sizeof(EnvPlan) +
-                           (2 * ST_TILES + ST_PLANS) * sizeof(uint64_t);
+                           (2 * ST_TILES + ST_PLANS + ST_NBUF) * sizeof(uint64_t);
 static_assert(sizeof(EnvPlan) == 48, "plan record layout");
 static_assert(ST_SMEM <= 227 * 1024, "shared memory budget");
 
