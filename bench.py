@@ -217,6 +217,7 @@ def main():
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the CUDA kernels are the only implementation (use --impl reference for the CPU arm)")
+    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")      # NCCL's banner / debug lines must not share stdout with the JSON line
     rank, local, world = init_from_env()
     dev = torch.device("cuda", local)
     _ffi.load()
