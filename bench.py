@@ -217,7 +217,11 @@ def main():
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the CUDA kernels are the only implementation (use --impl reference for the CPU arm)")
-    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")      # NCCL's banner / debug lines must not share stdout with the JSON line
+    # NCCL's banner / debug lines must not share stdout with the JSON line.  NCCL honours NCCL_DEBUG_FILE only above the VERSION
+    # level, so a VERSION setting (this image's default) is raised to WARN: same banner, now on stderr.
+    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+    if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+        os.environ["NCCL_DEBUG"] = "WARN"
     rank, local, world = init_from_env()
     dev = torch.device("cuda", local)
     _ffi.load()
