@@ -32,15 +32,14 @@ int check_launch(const char* what) {
     return PHC_OK;
 }
 
-int sm_count() {
-    static thread_local int cached = 0;
-    if (cached == 0) {
-        int dev = 0, n = 0;
-        if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0)
-            n = 148;   // B200
-        cached = n;
-    }
-    return cached;
+int sm_count() {      // cached per DEVICE (a process may drive several GPUs from one thread)
+    static int cached[64] = {0};
+    int dev = 0, n = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+    if (dev >= 0 && dev < 64 && cached[dev] > 0) return cached[dev];
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;   // B200
+    if (dev >= 0 && dev < 64) cached[dev] = n;
+    return n;
 }
 
 }  // namespace phc

@@ -11,6 +11,12 @@
 // output is bit-identical to the serial scan; chunks whose window reaches the end of the array are exact by
 // construction.  Tiles are staged in shared memory with coalesced loads/stores (stride-(CH+1) padding).
 // Serial kernel: one thread, used when gamma*lambda is too close to 1 for a bounded window.
+//
+// PRECONDITION of the blocked kernel (mode 0 picks it silently, mode 1 forces it): FINITE inputs.  In the reference's serial scan a
+// NaN / Inf in rewards or values poisons every earlier element up to the previous done; the blocked kernel would carry it only K
+// elements back, and a carry more than ~2^16 times larger than the local values can differ in the last bits.  Callers that must
+// reproduce the reference's behaviour on corrupted rollouts (core.py notes "Nans in adversarial reward and gae") use mode 2, which
+// is the reference's scan verbatim; tests/test_gpu_parity.py holds both modes to the serial result incl. NaN and large-magnitude cases.
 #include "phc_common.cuh"
 
 namespace phc {
@@ -131,11 +137,9 @@ extern "C" int phc_gae(const float* dones, const float* values, const float* rew
     if (ch == 8) {
         gae_blocked_kernel<8><<<(unsigned)tiles, GAE_THREADS, smem, s>>>(dones, values, rewards, L, gamma, gl, K, advantages);
     } else {
-        static thread_local size_t configured = 0;
-        if (smem > 48 * 1024 && smem > configured) {
+        if (smem > 48 * 1024) {      // per-device attribute and a cheap call: set it on every launch that needs it (no per-thread cache)
             cudaError_t e = cudaFuncSetAttribute(gae_blocked_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
             if (e != cudaSuccess) return fail((int)e, "%s: cudaFuncSetAttribute: %s", fn, cudaGetErrorString(e));
-            configured = smem;
         }
         gae_blocked_kernel<32><<<(unsigned)tiles, GAE_THREADS, smem, s>>>(dones, values, rewards, L, gamma, gl, K, advantages);
     }

@@ -157,6 +157,7 @@ __global__ void __launch_bounds__(256) rms_reduce_kernel(const double* __restric
 __global__ void rms_finalize_kernel(const double* __restrict__ moments, int C, float* __restrict__ running_mean,
                                     float* __restrict__ running_var, float* __restrict__ count) {
     const double n = moments[0];
+    if (!(n > 0.0)) return;         // nothing pending (double finalize, empty rollout): leave mean / var / count untouched (uniform exit)
     const float weight = 1.0f / count[0];
     for (int c = threadIdx.x; c < C; c += blockDim.x) {
         const double m = moments[1 + c] / n;

@@ -64,6 +64,9 @@ static_assert(ST_ENVS % 4 == 0 && ST_NBUF <= 32, "a compute group handles 4 envs
 #ifndef ST_A_WAITS_TILE
 #define ST_A_WAITS_TILE 0
 #endif
+#ifndef ST_STRESS_DELAY
+#define ST_STRESS_DELAY 0                            // test builds only: 1 = role B sleeps in every iteration, 2 = role A does, 3 = the writers do
+#endif                                               // (tests/test_fused_stress.py: outputs must stay bit-identical under any role skew)
 #ifndef ST_PLAN_EARLY
 #define ST_PLAN_EARLY 0                              // 1: the planner computes plan p before it waits for the ring slot -- no gain
 #endif                                               // (0.1745 vs 0.1729 ms): the plans are not what the critical role waits for
@@ -385,11 +388,18 @@ __global__ void __maxnreg__(ST_MAXREG) step_fused_kernel(const StepArgs a) {   /
                 cp_async_commit();
             }
             PROF_BEGIN
-            // tile buffer b released by the writers -- only role B writes tile rows; role A never waits for the writers (it cannot
-            // run more than two iterations ahead of role B anyway: its plans depend on full[] of both roles)
+            // tile buffer b released by the writers -- only role B writes tile rows, so only role B waits for the writers.
+            // Role A still must not ARRIVE on full[b] for this use before the previous phase of full[b] has completed: with
+            // ST_TILES = 2 its six arrivals of iteration it could otherwise pair up with its own six of iteration it - 2 while role B
+            // is still writing that older tile (the plan wait below holds role A back everywhere except in a CTA's last
+            // iteration, which has no next plan).  The wait is one try_wait that succeeds at once whenever role A is the slower role.
             if ((ST_A_WAITS_TILE || role == 1) && use >= 1) mbar_wait<ST_CHINT>(&empty[b], (use - 1) & 1);
+            else if (use >= 1) mbar_wait<ST_CHINT>(&full[b], (use - 1) & 1);
             PROF_END(2)
 
+#if ST_STRESS_DELAY == 1 || ST_STRESS_DELAY == 2
+            if (role == 2 - ST_STRESS_DELAY) __nanosleep(3000 + 997 * ((it * 7 + warp) % 5));
+#endif
             if (role == 0) {
                 // ============ role A: reward, reset, power (reference at t) ============
                 float* rj = red + (slot * NB + j) * 8;
@@ -533,6 +543,9 @@ __global__ void __maxnreg__(ST_MAXREG) step_fused_kernel(const StepArgs a) {   /
             const int64_t e0 = blk * ST_ENVS;
             const int rows = (int)((in.N - e0 < ST_ENVS) ? (in.N - e0) : ST_ENVS);
             mbar_wait<ST_WHINT>(&full[b], (it / ST_TILES) & 1);
+#if ST_STRESS_DELAY == 3
+            __nanosleep(4000 + 1000 * (it % 3));
+#endif
             // ---- raw observations: one TMA bulk store of the whole tile (manual copy for odd tails / pitched rows) ----
             const bool bulk = a.obs_vec && ((rows & 1) == 0);     // rows * 3736 B is a multiple of 16 for even rows
             if (bulk) {

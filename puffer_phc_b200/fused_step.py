@@ -157,7 +157,8 @@ class FusedStep:
             _ffi.check(self.lib.phc_step_fused(C.byref(self.motion_lib.ctables), C.byref(sin), C.byref(self._ccfg), C.byref(sout),
                                                _ffi.stream_ptr()), "phc_step_fused")
             if self.defer_moments:
-                self._pending_rows += N
+                if not torch.cuda.is_current_stream_capturing():      # a capture runs no kernel: replays are counted by count_replayed()
+                    self._pending_rows += N
             elif self.accumulate_moments:
                 self.rms.accumulate_partials(self.partials, N)
         res = {"obs": obs, "reward": rew, "reward_raw": raw, "reset": reset, "terminated": term}
@@ -243,6 +244,10 @@ class FusedStep:
         given, fixed input/output buffers into a CUDA graph.  Returns ``(graph, outputs)``; call ``graph.replay()`` each
         step after the simulator has refreshed the input buffers in place (as Isaac Gym does)."""
         args = (body_state, progress_buf, motion_start_times, motion_start_times_offset, sampled_motion_ids, global_offset, dof_force, dof_vel)
+        # the two warm-up calls below must leave no trace in the normaliser statistics: fold what is pending first, then discard
+        # the warm-up's contribution (per-CTA slots / pending moments) after it
+        self.flush_moments()
+        saved_moments = self.rms.moments_buffer().clone() if (self.accumulate_moments and self.rms is not None) else None
         side = torch.cuda.Stream(device=self.device)
         side.wait_stream(torch.cuda.current_stream(self.device))
         with torch.cuda.stream(side):
@@ -252,6 +257,12 @@ class FusedStep:
                     extra()
         torch.cuda.current_stream(self.device).wait_stream(side)
         torch.cuda.synchronize(self.device)
+        if self.accumulate_moments:
+            if self.defer_moments:
+                self.partials.zero_()
+                self._pending_rows = 0
+            if saved_moments is not None:
+                self.rms.moments_buffer().copy_(saved_moments)
         graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(graph):
             res = self(*args, out=out)
