@@ -14,8 +14,10 @@ One "step" = one pass of the hot path over one batch of N synthetic envs per GPU
 Inputs are resident in HBM before the timed region; four input/output sets are rotated so that neither the
 sim state nor the observation buffers are L2-resident between iterations.  The e2e leg runs the same step
 through FusedStep.step_host with pinned HOST buffers (H2D of every per-env input, D2H of reward / flags).
-`--impl reference` times the reference's torch-CPU path (oracle/torch_port.py, validated against the reference's
-golden vectors) on the host cores.  Nothing here reads /root/reference.
+`--impl reference` times the reference's OWN functions (the unmodified files build() stages under the git-ignored oracle/_ref/,
+run through oracle/ref_runner.py) on the host cores with all threads, on the same 65536-env workload; `cpu_baseline` is the same on
+a bounded number of steps, and `gpu_eager_baseline` runs the same reference functions with torch eager on the same B200.
+Nothing here reads /root/reference.
 """
 import argparse
 import json
@@ -104,70 +106,115 @@ def ncu_traffic(n_envs):
     return None
 
 
-def cpu_port_rate(n_envs, iters, warmup, threads, tables_host, seed=1):
-    """env-steps/s of the reference torch-CPU path (full step + RunningNorm.forward + the amortised c_gae share)."""
+def _reference_step_fn(tables_host, n_envs, device, seed=1):
+    """One reference 'step' on ``device`` = the reference's OWN functions (oracle/_ref staged by build(); oracle/ref_runner.py): the
+    post-physics half of HumanoidPHC.step + RunningNorm.forward + the amortised c_gae share (host numpy round trip included on CUDA,
+    as in clean_pufferl/core.py:242-253).  Falls back to the torch port (oracle/torch_port.py) when oracle/_ref is absent.
+    Returns (callable, kind, description)."""
     import numpy as np
     import torch
-    from oracle import c_oracle, torch_port as tp
+    from oracle import c_oracle, ref_runner as rr, torch_port as tp
     from puffer_phc_b200 import synth
-    torch.set_num_threads(threads)
     S = synth.make_env_state(tables_host, n_envs, seed=seed)
     R = synth.make_rollout(max(n_envs // HORIZON, 1), HORIZON, seed=2)
     d, v, r = (R[k].numpy() for k in ("dones", "values", "rewards"))
+    dev = torch.device(device)
+    if rr.available():
+        Rm = rr.boot()
+        lib = rr.lib_from_tables(tables_host, dev)
+        Sd = {k: t.to(dev) for k, t in S.items()}
+        rn = Rm.rn.RunningNorm(934).to(dev)
+        gae = Rm.c_gae.compute_gae if Rm.c_gae is not None else (lambda *a: c_oracle.gae(*a))
+        vd, rd, dd = (torch.from_numpy(x).to(dev) for x in (v, r, d))
+
+        def fn():
+            out = rr.step(lib, Sd)
+            y = rn(out["obs"])
+            if dev.type == "cuda":          # the reference's GAE lives on the host: values / rewards / dones go down, advantages come back
+                adv = gae(dd.cpu().numpy(), vd.cpu().numpy(), rd.cpu().numpy(), 0.98, 0.2)
+                torch.from_numpy(np.asarray(adv)).to(dev)
+            else:
+                gae(d, v, r, 0.98, 0.2)
+            return y
+        what = ("the reference's own torch functions (oracle/_ref: motion_lib.get_motion_state x2, envs/common.compute_* , "
+                "policies/running_norm.RunningNorm.forward) + its compiled c_gae.pyx" if Rm.c_gae is not None else
+                "the reference's own torch functions (oracle/_ref) + C c_gae restatement")
+        return fn, "reference", what
     mean, var = torch.zeros(1, 934), torch.ones(1, 934)
-    times = []
-    for i in range(warmup + iters):
-        t0 = time.perf_counter()
+    if dev.type != "cpu":
+        raise RuntimeError("the torch port is a CPU baseline only")
+
+    def fn_port():
         out = tp.step(tables_host, S)
         tp.rms_forward(out["obs"], mean, var)
         c_oracle.gae(d, v, r, 0.98, 0.2)
+    return fn_port, "port", "torch-CPU eager port of the reference functions (oracle/torch_port.py) + C c_gae restatement"
+
+
+def cpu_reference_rate(n_envs, iters, warmup, threads, tables_host, seed=1):
+    """env-steps/s of the reference path on the host cores (full step + RunningNorm.forward + the amortised c_gae share)."""
+    import torch
+    torch.set_num_threads(threads)
+    fn, kind, what = _reference_step_fn(tables_host, n_envs, "cpu", seed)
+    times = []
+    for i in range(warmup + iters):
+        t0 = time.perf_counter()
+        fn()
         dt = time.perf_counter() - t0
         if i >= warmup:
             times.append(dt)
-    return n_envs / statistics.median(times), sum(times)
+    return n_envs / statistics.median(times), sum(times), kind, what
+
+
+def gpu_eager_rate(n_envs, iters, warmup, tables_host, dev, seed=1):
+    """env-steps/s of the SAME reference functions run by torch eager / TorchScript on the same GPU (what a user of the reference
+    gets on this B200 today), CUDA-event timed."""
+    import torch
+    from oracle import ref_runner as rr
+    if not rr.available():
+        return None
+    fn, kind, what = _reference_step_fn(tables_host, n_envs, dev, seed)
+    for _ in range(warmup):
+        fn()
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(iters):
+        fn()
+    b.record()
+    torch.cuda.synchronize()
+    ms = a.elapsed_time(b) / iters
+    return {"value": n_envs / (ms * 1e-3), "unit": "env-steps/s", "ms_per_step": ms, "kind": "reference",
+            "sample": f"{n_envs} envs x {iters} steps after {warmup} warm-ups (TorchScript profiling runs included in the warm-up), "
+                      f"torch {torch.__version__} eager on the same GPU: {what}; GAE as the reference does it (host round trip)"}
 
 
 def run_reference(args, rank, world):
-    """The reference arm: the reference's own CPU implementation of the path (torch eager port), all host threads."""
+    """The reference arm: the reference's own CPU implementation of the path, all host threads, on the bench's own config
+    (the full ``--envs`` batch per step: same workload as our arm)."""
     if rank != 0:
         return
     import torch
     from puffer_phc_b200 import synth
     threads = os.cpu_count() or 1
-    sample = 8192
-    T = synth.make_motion_library(NUM_CLIPS, seed=0, device="cpu")
     torch.set_num_threads(threads)
-    import statistics as st
-    from oracle import c_oracle, torch_port as tp
-    S = synth.make_env_state(T, sample, seed=1)
-    R = synth.make_rollout(sample // HORIZON, HORIZON, seed=2)
-    d, v, r = (R[k].numpy() for k in ("dones", "values", "rewards"))
-    mean, var = torch.zeros(1, 934), torch.ones(1, 934)
-    gae_fn, gae_kind = (lambda: c_oracle.gae(d, v, r, 0.98, 0.2)), "C c_gae restatement"
-    try:                                     # the reference's OWN c_gae.pyx, compiled into oracle/_ref/ by build() where the reference exists
-        sys.path.insert(0, os.path.join(ROOT, "oracle", "_ref"))
-        import c_gae as ref_c_gae
-        gae_fn, gae_kind = (lambda: ref_c_gae.compute_gae(d, v, r, 0.98, 0.2)), "the reference's own c_gae.pyx (oracle/_ref)"
-    except Exception:
-        pass
+    T = synth.make_motion_library(NUM_CLIPS, seed=0, device="cpu")
+    fn, kind, what = _reference_step_fn(T, args.envs, "cpu")
     times = []
     for i in range(args.warmup + args.steps):
         t0 = time.perf_counter()
-        out = tp.step(T, S)
-        tp.rms_forward(out["obs"], mean, var)
-        gae_fn()
+        fn()
         if i >= args.warmup:
             times.append(time.perf_counter() - t0)
     total = sum(times)
-    value = sample * len(times) / total
+    value = args.envs * len(times) / total
     line = {
         "impl": "reference", "metric": "env_steps_per_s", "value": value, "unit": "env-steps/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / len(times), "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": workload_config(args.envs, world, sample_note=f"each step = a bounded sample of {sample} envs of the workload"),
-        "cpu_baseline": {"value": value, "unit": "env-steps/s", "cores": threads, "kind": "port",
-                         "sample": f"{sample} envs x {len(times)} steps, torch {torch.__version__} eager CPU port of the reference "
-                                   f"functions (oracle/torch_port.py) + {gae_kind}"},
+        "config": workload_config(args.envs, world),
+        "cpu_baseline": {"value": value, "unit": "env-steps/s", "cores": threads, "kind": kind,
+                         "sample": f"{args.envs} envs x {len(times)} steps, torch {torch.__version__} CPU, {threads} threads: {what}"},
         "e2e": {"value": value, "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -197,6 +244,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-gpu-eager", action="store_true")
     ap.add_argument("--no-other-configs", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
@@ -401,11 +449,11 @@ def main():
         if world == 1 and not args.no_cpu_baseline:
             threads = os.cpu_count() or 1
             host_tables = {k: v.cpu() for k, v in T.items()}
-            sample = N
-            rate, spent = cpu_port_rate(sample, iters=20, warmup=2, threads=threads, tables_host=host_tables)
-            line["cpu_baseline"] = {"value": rate, "unit": "env-steps/s", "cores": threads, "kind": "port",
-                                    "sample": f"{sample} envs x 20 steps of the same workload ({spent:.1f} s), torch-CPU eager port of the "
-                                              "reference functions (oracle/torch_port.py) + C c_gae restatement"}
+            rate, spent, kind, what = cpu_reference_rate(N, iters=10, warmup=2, threads=threads, tables_host=host_tables)
+            line["cpu_baseline"] = {"value": rate, "unit": "env-steps/s", "cores": threads, "kind": kind,
+                                    "sample": f"{N} envs x 10 steps of the same workload ({spent:.1f} s): {what}"}
+            if not args.no_gpu_eager:
+                line["gpu_eager_baseline"] = gpu_eager_rate(N, iters=10, warmup=4, tables_host=host_tables, dev=dev)
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define PHC_B200_VERSION 100 /* 0.1.0 */
+#define PHC_B200_VERSION 110 /* 0.1.1 */
 
 enum {
     PHC_OK = 0,
@@ -41,6 +41,14 @@ enum {
     PHC_ESHAPE = -3,       /* J, C or L outside the supported range                           */
     PHC_EUNSUPPORTED = -4  /* semantically valid in the reference but not implemented (e.g. time_steps != 1) */
 };
+
+/* REFERENCE DEVICE FLAVOUR.  The reference runs this path with torch on CUDA (puffer_phc/envs/humanoid_phc.py) but can also be
+ * run on the CPU (where the committed golden vectors were made).  torch rounds three small reductions differently on the two
+ * devices -- torch.sum(q0*q1,-1) inside slerp (torch_utils.py:113), torch.norm(.., dim=-1) over xyz in the termination test
+ * (envs/common.py:343) and .mean(-1) of the eval variant (:344) -- plus tensor / python-scalar in sample_time_interval
+ * (motion_lib.py:533).  All four were fitted bit-exactly on the B200 box (profiles/r2_torch_device_flavours.md).  Every entry
+ * point that contains one takes `ref_device` and reproduces that device's rounding, so flags are bit-exact against either. */
+enum { PHC_REF_DEVICE_CPU = 0, PHC_REF_DEVICE_CUDA = 1 };
 
 typedef void *phc_stream_t; /* cudaStream_t */
 
@@ -171,7 +179,7 @@ typedef struct phc_motion_state_out {
 
 int phc_motion_state(const phc_motion_tables *t, const int64_t *motion_ids, const float *motion_times,
                      const float *offset /* [B,3] or NULL */, int64_t B, const phc_motion_state_out *out,
-                     phc_stream_t stream);
+                     int ref_device, phc_stream_t stream);
 
 /* Reset path ("next" row f1): HumanoidPHC._sample_ref_state + _set_env_state for the envs listed in env_ids
  * (puffer_phc/envs/humanoid_phc.py:843-873, 899-929): one get_motion_state query per reset env
@@ -184,7 +192,7 @@ int phc_motion_state(const phc_motion_tables *t, const int64_t *motion_ids, cons
 int phc_reset_ref_state(const phc_motion_tables *t, const int64_t *env_ids, const int64_t *sampled_motion_ids /* [N] */,
                         const float *motion_times /* [K] */, const float *global_offset /* [N,3] or NULL */, int64_t K,
                         float *root_states, float *dof_pos, float *dof_vel, float *body_state, int64_t env_stride,
-                        phc_stream_t stream);
+                        int ref_device, phc_stream_t stream);
 
 /* MotionLibBase._calc_frame_blend(time, len, num_frames, dt) (puffer_phc/motion_lib.py:655-665), elementwise over n entries:
  * phase = clip(time/len, 0, 1); time < 0 -> 0; idx0 = int64(phase * (nf-1)); idx1 = min(idx0+1, nf-1);
@@ -194,8 +202,8 @@ int phc_frame_blend(const float *time, const float *len, const int64_t *num_fram
 
 /* MotionLibBase.sample_time_interval arithmetic (puffer_phc/motion_lib.py:526-535); the uniform
  * phase stays on the caller's torch generator.  out = float(int64((phase*len)/(1/30))) * (1/30).
- * div_mode 0: IEEE division (torch CPU); 1: multiply by fp32 reciprocal (torch CUDA divides a
- * tensor by a Python scalar that way).  motion_len is already gathered per sample. */
+ * div_mode = ref_device: 0 IEEE division by float32(1/30) (torch CPU); 1 multiplication by float(1.0 / (1/30)) = 30.0f, the
+ * reciprocal formed in double (how torch CUDA divides a tensor by a Python scalar).  motion_len is already gathered per sample. */
 int phc_sample_time_interval(const float *phase, const float *motion_len, int64_t n, int div_mode, float *out,
                              phc_stream_t stream);
 
@@ -231,11 +239,11 @@ int phc_imitation_reward(phc_view body_pos, phc_view body_rot, phc_view body_vel
  * (only element 0 is read when use_mean). */
 int phc_im_reset(const int16_t *progress, phc_view rigid_body_pos, phc_view ref_body_pos, const uint8_t *pass_time,
                  int enable_early_termination, const float *termination_distance, int use_mean,
-                 int64_t N, int J, uint8_t *reset, uint8_t *terminated, phc_stream_t stream);
+                 int64_t N, int J, uint8_t *reset, uint8_t *terminated, int ref_device, phc_stream_t stream);
 
 /* The evaluation metric HumanoidPHC.step adds when flag_im_eval is set (puffer_phc/envs/humanoid_phc.py:159-163, consumed by
  * EvalStats, scripts/train.py:139-166): mpjpe[n] = mean_j || body_pos[n,j] - ref_body_pos[n,j] ||, ref = rg_pos at t. */
-int phc_mpjpe(phc_view body_pos, phc_view ref_body_pos, int64_t N, int J, float *mpjpe, phc_stream_t stream);
+int phc_mpjpe(phc_view body_pos, phc_view ref_body_pos, int64_t N, int J, float *mpjpe, int ref_device, phc_stream_t stream);
 
 /* build_amp_observations_smpl + dof_to_obs_smpl (common.py:179-267; "next" row f3, only used with use_amp_obs) without the
  * shape / limb-weight pass-through columns.  Contiguous inputs: root_* [N,3|4], dof_pos / dof_vel [N,69], key_body_pos [N,K,3];
@@ -244,7 +252,7 @@ int phc_mpjpe(phc_view body_pos, phc_view ref_body_pos, int64_t N, int J, float 
 int phc_amp_obs_smpl(const float *root_pos, const float *root_rot, const float *root_vel, const float *root_ang_vel,
                      const float *dof_pos, const float *dof_vel, const float *key_body_pos, const int64_t *dof_subset,
                      int num_joints, int K, int local_root_obs, int root_height_obs, int upright, int64_t N, float *obs,
-                     int64_t obs_stride, phc_stream_t stream);
+                     int64_t obs_stride, int ref_device, phc_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------- */
 /* The whole post-physics half of HumanoidPHC.step in ONE pass over HBM                          */
@@ -278,6 +286,8 @@ typedef struct phc_step_cfg {
     int enable_early_termination;
     int use_mean;                /* flag_im_eval: mean distance against term_dist[first reset body]        */
     float rms_eps, rms_clip;     /* RunningNorm epsilon / clip (running_norm.py:6)                         */
+    int ref_device;              /* PHC_REF_DEVICE_CPU / _CUDA: whose rounding the slerp dot product, the termination norm
+                                    and the eval-mode mean reproduce                                       */
 } phc_step_cfg;
 
 typedef struct phc_step_out {

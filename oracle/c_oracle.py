@@ -43,6 +43,11 @@ def lib() -> C.CDLL:
     return _lib
 
 
+def set_ref_device(kind) -> None:
+    """Whose torch rounding the oracle's device-dependent reductions follow: "cpu" (default; the golden vectors) or "cuda"."""
+    lib().phc_oracle_set_ref_device(1 if kind in ("cuda", 1) else 0)
+
+
 class _Tables(C.Structure):
     _fields_ = [(k, C.c_void_p) for k in TABLE_KEYS] + [("F", C.c_int64), ("M", C.c_int64)]
 

@@ -127,11 +127,51 @@ static v3 o_quat_to_exp_map(q4 q)
     return r;
 }
 
+/* REFERENCE DEVICE FLAVOUR (test infrastructure state): torch rounds three small reductions of this path differently on CPU and on
+ * CUDA; both orders were fitted bit-exactly against torch 2.11 on the B200 box (profiles/r2_torch_device_flavours.md):
+ *   torch.sum(q0*q1,-1) over 4 (torch_utils.py:113)   CPU ((p0+p1)+p2)+p3              CUDA (p0+p2)+(p1+p3)
+ *   torch.norm(d,dim=-1) over 3 (common.py:343)        CPU sqrt(fma(z,z,fma(y,y,x*x)))  CUDA sqrt((x*x+z*z)+y*y)
+ *   .mean(-1) over J (common.py:344)                   CPU 8 lanes + tail first, / J    CUDA lane tree * float(1/J)
+ *   tensor / python scalar (motion_lib.py:533)         CPU IEEE division                CUDA * float(1.0/scalar)
+ * 0 = CPU (the device the golden vectors were made on), 1 = CUDA. */
+static int g_ref_device = 0;
+void phc_oracle_set_ref_device(int dev) { g_ref_device = dev ? 1 : 0; }
+int phc_oracle_get_ref_device(void) { return g_ref_device; }
+
+static float o_dot4(q4 a, q4 b)
+{
+    float p0 = a.x * b.x, p1 = a.y * b.y, p2 = a.z * b.z, p3 = a.w * b.w;
+    return g_ref_device ? (p0 + p2) + (p1 + p3) : ((p0 + p1) + p2) + p3;
+}
+
+/* .mean(-1) over n <= 32 values in the selected device's order */
+static float o_mean(const float *v, int n)
+{
+    if (!g_ref_device) {   /* torch CPU: 8 vector lanes over the full rows of 8, scalar tail first, then the lanes one by one; / n */
+        const int full = (n / 8) * 8;
+        float s = 0.0f;
+        for (int i = full; i < n; ++i) s = (i == full) ? v[i] : s + v[i];
+        for (int k = 0; k < 8 && k < full; ++k) {
+            float a = v[k];
+            for (int i = k + 8; i < full; i += 8) a = a + v[i];
+            s = (k == 0 && full == n) ? a : s + a;
+        }
+        return s / (float)n;
+    }
+    int bx = 1;
+    while (bx * 2 <= n) bx *= 2;
+    float t[32];
+    for (int k = 0; k < bx; ++k) t[k] = (k + bx < n) ? v[k] + v[k + bx] : v[k];
+    for (int off = bx / 2; off >= 1; off /= 2)
+        for (int k = 0; k < off; ++k) t[k] = t[k] + t[k + off];
+    return t[0] * (1.0f / (float)n);
+}
+
 /* torch_utils.py:110-131 slerp.  No renormalisation; the two torch.where fall-backs
  * are applied in the reference's order (lerp when |sin|<1e-3, then q0 when |cos|>=1). */
 static q4 o_slerp(q4 q0, q4 q1, float t)
 {
-    float c = ((q0.x * q1.x + q0.y * q1.y) + q0.z * q1.z) + q0.w * q1.w;
+    float c = o_dot4(q0, q1);
     if (c < 0.0f) { q1.x = -q1.x; q1.y = -q1.y; q1.z = -q1.z; q1.w = -q1.w; }
     c = fabsf(c);
     float h = acosf(c);
@@ -258,11 +298,11 @@ int phc_oracle_motion_state(const phc_oracle_tables *T, const int64_t *ids, cons
 
 /* motion_lib.py:526-535 sample_time_interval arithmetic (the torch.rand phase is an input).
  * div_mode 0: CPU torch true division by float32(1/30); 1: torch-CUDA's scalar fast path,
- * multiplication by float32(1/float32(1/30)). */
+ * multiplication by float(1.0 / (1/30)) = 30.0f (the reciprocal is formed in double; fitted bit-exactly on the box). */
 int phc_oracle_sample_time_interval(const float *phase, const float *motion_len, int64_t n, int div_mode, float *out)
 {
     const float fps = (float)(1.0 / 30.0);
-    const float inv = 1.0f / fps;
+    const float inv = (float)(1.0 / (1.0 / 30.0));
     for (int64_t i = 0; i < n; ++i) {
         float x = phase[i] * motion_len[i];
         float q = div_mode ? x * inv : x / fps;
@@ -387,7 +427,11 @@ int phc_oracle_imitation_reward(const float *body_pos, const float *body_rot, co
     return 0;
 }
 
-static float o_norm3(v3 d) { return sqrtf(fmaf(d.z, d.z, fmaf(d.y, d.y, d.x * d.x))); }
+static float o_norm3(v3 d)
+{
+    if (g_ref_device) return sqrtf((d.x * d.x + d.z * d.z) + d.y * d.y);
+    return sqrtf(fmaf(d.z, d.z, fmaf(d.y, d.y, d.x * d.x)));
+}
 
 /* common.py:325-364 compute_humanoid_im_reset. progress is int16 (humanoid_phc.py:571). */
 int phc_oracle_im_reset(const int16_t *progress, const float *body_pos, const float *ref_pos, const uint8_t *pass_time,
@@ -399,9 +443,9 @@ int phc_oracle_im_reset(const int16_t *progress, const float *body_pos, const fl
         int fallen = 0;
         if (enable_early_termination) {
             if (use_mean) {                                                         /* :342-346 */
-                float s = 0.0f;
-                for (int j = 0; j < J; ++j) s += o_norm3(v3sub(ldv(body_pos + (i * J + j) * 3), ldv(ref_pos + (i * J + j) * 3)));
-                fallen = (s / (float)J) > term_dist[0];
+                float dj[32];
+                for (int j = 0; j < J; ++j) dj[j] = o_norm3(v3sub(ldv(body_pos + (i * J + j) * 3), ldv(ref_pos + (i * J + j) * 3)));
+                fallen = o_mean(dj, J) > term_dist[0];
             } else {                                                                /* :347-350 */
                 for (int j = 0; j < J; ++j)
                     fallen |= o_norm3(v3sub(ldv(body_pos + (i * J + j) * 3), ldv(ref_pos + (i * J + j) * 3))) > term_dist[j];
@@ -418,9 +462,9 @@ int phc_oracle_im_reset(const int16_t *progress, const float *body_pos, const fl
 int phc_oracle_mpjpe(const float *body_pos, const float *ref_pos, int64_t N, int J, float *out)
 {
     for (int64_t i = 0; i < N; ++i) {
-        float s = 0.0f;
-        for (int j = 0; j < J; ++j) s += o_norm3(v3sub(ldv(body_pos + (i * J + j) * 3), ldv(ref_pos + (i * J + j) * 3)));
-        out[i] = s / (float)J;
+        float dj[32];
+        for (int j = 0; j < J; ++j) dj[j] = o_norm3(v3sub(ldv(body_pos + (i * J + j) * 3), ldv(ref_pos + (i * J + j) * 3)));
+        out[i] = o_mean(dj, J);
     }
     return 0;
 }

@@ -104,7 +104,7 @@ def load_cmu(device="cpu"):
 
 
 def step(lib, S: Dict[str, torch.Tensor], eval_mode: bool = False, power: bool = True, with_blend: bool = False,
-         full_state: bool = False) -> Dict[str, torch.Tensor]:
+         full_state: bool = False, eval_distance: float = 0.5) -> Dict[str, torch.Tensor]:
     """The post-physics half of ``HumanoidPHC.step`` (humanoid_phc.py:136-149) on the reference's functions, on the device the
     inputs live on.  ``S``: body_state [N,B,13], progress i16, start_time, start_offset, motion_ids, global_offset (+ dof_force /
     dof_vel).  Returns obs [N,934], reward, reward_raw, reset, terminated (+ optional extras)."""
@@ -144,7 +144,7 @@ def step(lib, S: Dict[str, torch.Tensor], eval_mode: bool = False, power: bool =
     contact = torch.zeros(len(ids), 24, 3, device=dev)
     cids = torch.zeros(4, dtype=torch.long, device=dev)
     if eval_mode:
-        td = torch.full((24,), 0.5, device=dev)
+        td = torch.full((24,), float(eval_distance), device=dev)
         rs, tm = common.compute_humanoid_im_reset(reset_buf, prog, contact, cids, body_pos[..., EVAL_BODY_IDS, :],
                                                   r0["rg_pos"][..., EVAL_BODY_IDS, :], pass_time, True, td[..., EVAL_BODY_IDS], True)
     else:

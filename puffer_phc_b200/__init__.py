@@ -11,4 +11,6 @@ Drop-in modules mirror the reference's call surface:
 All arithmetic runs in hand-written CUDA kernels behind the C-ABI library ``libphc_b200.so``
 (include/phc_b200.h).  There is no CPU fallback: every entry point raises if the library is missing.
 """
-__version__ = "0.1.0"
+from ._ffi import set_reference_device  # noqa: E402,F401  ("cuda" default | "cpu": whose torch rounding flags reproduce)
+
+__version__ = "0.1.1"

@@ -23,6 +23,8 @@ EXPORTS = (
     "phc_rms_reduce_partials", "phc_rms_finalize", "phc_gae", "phc_build_motion_tables", "phc_build_motion_aa", "phc_cast_f64_f32", "phc_mpjpe", "phc_frame_blend",
 )
 
+VERSION = 110
+REF_CPU, REF_CUDA = 0, 1
 PHC_OK, PHC_EINVAL, PHC_EALIGN, PHC_ESHAPE, PHC_EUNSUPPORTED = 0, -1, -2, -3, -4
 
 
@@ -59,7 +61,7 @@ class StepCfg(C.Structure):
     _fields_ = [
         ("dt", C.c_float), ("k", C.c_float * 4), ("w", C.c_float * 4), ("power_coef", C.c_float),
         ("reset_body_mask", C.c_uint32), ("enable_early_termination", C.c_int), ("use_mean", C.c_int),
-        ("rms_eps", C.c_float), ("rms_clip", C.c_float),
+        ("rms_eps", C.c_float), ("rms_clip", C.c_float), ("ref_device", C.c_int),
     ]
 
 
@@ -90,14 +92,14 @@ def _declare(lib):
     lib.phc_version.argtypes, lib.phc_version.restype = [], I
     lib.phc_last_error.argtypes, lib.phc_last_error.restype = [], C.c_char_p
     lib.phc_pack_frames.argtypes = [C.POINTER(MotionTables), P, P]
-    lib.phc_motion_state.argtypes = [C.POINTER(MotionTables), P, P, P, I64, C.POINTER(MotionStateOut), P]
-    lib.phc_reset_ref_state.argtypes = [C.POINTER(MotionTables), P, P, P, P, I64, P, P, P, P, I64, P]
+    lib.phc_motion_state.argtypes = [C.POINTER(MotionTables), P, P, P, I64, C.POINTER(MotionStateOut), I, P]
+    lib.phc_reset_ref_state.argtypes = [C.POINTER(MotionTables), P, P, P, P, I64, P, P, P, P, I64, I, P]
     lib.phc_sample_time_interval.argtypes = [P, P, I64, I, P, P]
     lib.phc_imitation_obs_v6.argtypes = [View] * 10 + [I64, I, I, I, P, I64, P]
     lib.phc_self_obs_smpl_max.argtypes = [View] * 4 + [I64, I, I, I, I, P, I64, P]
-    lib.phc_amp_obs_smpl.argtypes = [P] * 8 + [I, I, I, I, I, I64, P, I64, P]
+    lib.phc_amp_obs_smpl.argtypes = [P] * 8 + [I, I, I, I, I, I64, P, I64, I, P]
     lib.phc_imitation_reward.argtypes = [View] * 8 + [I64, I, C.POINTER(F), C.POINTER(F), P, P, I64, P]
-    lib.phc_im_reset.argtypes = [P, View, View, P, I, P, I, I64, I, P, P, P]
+    lib.phc_im_reset.argtypes = [P, View, View, P, I, P, I, I64, I, P, P, I, P]
     lib.phc_step_num_partials.argtypes, lib.phc_step_num_partials.restype = [], I
     lib.phc_step_fused.argtypes = [C.POINTER(MotionTables), C.POINTER(StepIn), C.POINTER(StepCfg), C.POINTER(StepOut), P]
     lib.phc_rms_forward.argtypes = [P, I64, P, P, F, F, I64, I, P, I64, P]
@@ -109,12 +111,41 @@ def _declare(lib):
     lib.phc_build_motion_tables.argtypes = [C.POINTER(BuildIn), C.POINTER(BuildOut), P]
     lib.phc_build_motion_aa.argtypes = [P, I, P, P, I64, I64, P, P, P, P, P]
     lib.phc_cast_f64_f32.argtypes = [P, I64, P, P]
-    lib.phc_mpjpe.argtypes = [View, View, I64, I, P, P]
+    lib.phc_mpjpe.argtypes = [View, View, I64, I, P, I, P]
     lib.phc_frame_blend.argtypes = [P, P, P, P, I64, P, P, P, P]
     for name in EXPORTS:
         fn = getattr(lib, name)
         if fn.restype is C.c_int and name not in ("phc_version", "phc_step_num_partials"):
             fn.restype = I
+
+
+# ---- reference device flavour (include/phc_b200.h: PHC_REF_DEVICE_*) ---------------------------------------------------
+# The drop-in functions keep the reference's signatures, so the flavour they reproduce is a package-level setting.  Default: CUDA,
+# the device the reference runs this path on; the committed golden vectors were made with torch-CPU, tests select "cpu" for those.
+_ref_device = REF_CUDA
+
+
+def set_reference_device(kind) -> int:
+    """Select whose rounding flag-deciding reductions reproduce: ``"cuda"`` (default) or ``"cpu"``.  Returns the previous value."""
+    global _ref_device
+    prev = _ref_device
+    if kind in ("cpu", REF_CPU):
+        _ref_device = REF_CPU
+    elif kind in ("cuda", REF_CUDA):
+        _ref_device = REF_CUDA
+    else:
+        raise ValueError(f"reference device must be 'cpu' or 'cuda', got {kind!r}")
+    return prev
+
+
+def ref_device(override=None) -> int:
+    if override is None:
+        return _ref_device
+    if override in ("cpu", REF_CPU):
+        return REF_CPU
+    if override in ("cuda", REF_CUDA):
+        return REF_CUDA
+    raise ValueError(f"reference device must be 'cpu' or 'cuda', got {override!r}")
 
 
 def library_path() -> str:
@@ -139,7 +170,7 @@ def load() -> C.CDLL:
                             "implementation of this package -- there is no CPU fallback") from exc
             lib = C.CDLL(path)
             _declare(lib)
-            if lib.phc_version() != 100:
+            if lib.phc_version() != VERSION:
                 raise RuntimeError(f"libphc_b200.so version {lib.phc_version()} does not match the Python package")
             _lib = lib
     return _lib

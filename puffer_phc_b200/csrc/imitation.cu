@@ -18,6 +18,15 @@ constexpr int IM_WARPS = 4;
 
 __device__ __forceinline__ const float* at(const phc_view& v, int64_t n, int j) { return v.ptr + n * v.stride_env + (int64_t)j * v.stride_body; }
 
+// .mean(dim=-1) over the J <= 32 lane values d in torch's summation order for the chosen device (phc_math.cuh mean_ordered); the
+// result is valid in every lane.  Only the eval-mode paths (use_mean, mpjpe) come here.
+__device__ __forceinline__ float warp_mean(float d, int J, int lane, int dev) {
+    float v[32];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = __shfl_sync(FULL, d, i);
+    return mean_ordered(v, J, dev);
+}
+
 constexpr int IM_REC = 32 * REC;          // floats of staging per warp (J <= 32 bodies x 13)
 
 // coalesced copy of one env's AoS record (nfl floats) into the warp's shared-memory buffer
@@ -125,7 +134,7 @@ __global__ void __launch_bounds__(IM_WARPS * 32) reward_kernel(const RewardArgs 
 
 struct ResetArgs {
     const int16_t* progress; phc_view pos, rpos; const uint8_t* pass_time; int early; const float* term_dist; int use_mean;
-    int64_t N; int J; uint8_t* reset; uint8_t* terminated;
+    int64_t N; int J; uint8_t* reset; uint8_t* terminated; int dev;
 };
 
 template <bool AOS>      // AOS: rigid_body_pos is the pos slice of the 13-float records (stride_body 13): stage the span coalesced
@@ -141,10 +150,10 @@ __global__ void __launch_bounds__(IM_WARPS * 32) reset_kernel(const ResetArgs a)
         float d = 0.0f;
         bool over = false;
         if (lane < a.J) {
-            d = norm3((AOS ? ld3(rec + REC * lane) : ld3(at(a.pos, n, lane))) - ld3(at(a.rpos, n, lane)));
+            d = norm3((AOS ? ld3(rec + REC * lane) : ld3(at(a.pos, n, lane))) - ld3(at(a.rpos, n, lane)), a.dev);
             over = d > __ldg(a.term_dist + (a.use_mean ? 0 : lane));
         }
-        if (a.use_mean) fallen = (warp_sum(d) / (float)a.J) > __ldg(a.term_dist);   // common.py:342-346
+        if (a.use_mean) fallen = warp_mean(d, a.J, lane, a.dev) > __ldg(a.term_dist);   // common.py:342-346
         else fallen = __any_sync(FULL, over);                                          // common.py:347-350
         fallen = fallen && (a.progress[n] > 1);                                        // common.py:354
     }
@@ -156,16 +165,16 @@ __global__ void __launch_bounds__(IM_WARPS * 32) reset_kernel(const ResetArgs a)
 
 // Evaluation metric of HumanoidPHC.step (reference puffer_phc/envs/humanoid_phc.py:159-163):
 // mpjpe = (body_pos - rg_pos).norm(dim=-1).mean(dim=-1).  One warp per env, lane = body.
-struct MpjpeArgs { phc_view pos, rpos; int64_t N; int J; float* out; };
+struct MpjpeArgs { phc_view pos, rpos; int64_t N; int J; float* out; int dev; };
 
 __global__ void __launch_bounds__(IM_WARPS * 32) mpjpe_kernel(const MpjpeArgs a) {
     const int lane = threadIdx.x & 31;
     const int64_t n = (int64_t)blockIdx.x * IM_WARPS + (threadIdx.x >> 5);
     if (n >= a.N) return;
     float d = 0.0f;
-    if (lane < a.J) d = norm3(ld3(at(a.pos, n, lane)) - ld3(at(a.rpos, n, lane)));
-    d = warp_sum(d);
-    if (lane == 0) a.out[n] = d / (float)a.J;
+    if (lane < a.J) d = norm3(ld3(at(a.pos, n, lane)) - ld3(at(a.rpos, n, lane)), a.dev);
+    d = warp_mean(d, a.J, lane, a.dev);
+    if (lane == 0) a.out[n] = d;
 }
 
 // build_amp_observations_smpl + dof_to_obs_smpl (reference envs/common.py:179-267), "next" row f3.
@@ -173,7 +182,7 @@ __global__ void __launch_bounds__(IM_WARPS * 32) mpjpe_kernel(const MpjpeArgs a)
 // the root terms and the key-body positions are spread over the first lanes.
 struct AmpArgs {
     const float *root_pos, *root_rot, *root_vel, *root_ang, *dof_pos, *dof_vel, *key_pos;
-    const int64_t* subset; int nj, K, local_root_obs, root_height_obs, upright; int64_t N; float* obs; int64_t obs_stride;
+    const int64_t* subset; int nj, K, local_root_obs, root_height_obs, upright; int64_t N; float* obs; int64_t obs_stride; int dev;
 };
 
 __global__ void __launch_bounds__(IM_WARPS * 32) amp_obs_kernel(const AmpArgs a) {
@@ -201,7 +210,7 @@ __global__ void __launch_bounds__(IM_WARPS * 32) amp_obs_kernel(const AmpArgs a)
             e[c] = __ldg(a.dof_pos + n * NDOF + idx);
             v[c] = __ldg(a.dof_vel + n * NDOF + idx);
         }
-        tan_norm(exp_map_to_quat(V3{e[0], e[1], e[2]}), dobs + 6 * j);                        // :186, 248
+        tan_norm(exp_map_to_quat(V3{e[0], e[1], e[2]}, a.dev), dobs + 6 * j);                        // :186, 248
         dvel[3 * j] = v[0]; dvel[3 * j + 1] = v[1]; dvel[3 * j + 2] = v[2];
     }
     for (int k = lane; k < a.K; k += 32)                                                      // :228-242
@@ -268,7 +277,7 @@ extern "C" int phc_self_obs_smpl_max(phc_view body_pos, phc_view body_rot, phc_v
 extern "C" int phc_amp_obs_smpl(const float* root_pos, const float* root_rot, const float* root_vel, const float* root_ang_vel,
                                 const float* dof_pos, const float* dof_vel, const float* key_body_pos, const int64_t* dof_subset,
                                 int num_joints, int K, int local_root_obs, int root_height_obs, int upright, int64_t N, float* obs,
-                                int64_t obs_stride, phc_stream_t stream) {
+                                int64_t obs_stride, int ref_device, phc_stream_t stream) {
     const char* fn = "phc_amp_obs_smpl";
     PHC_REQUIRE(N >= 0, PHC_EINVAL, "%s: N < 0", fn);
     PHC_REQUIRE(num_joints >= 0 && num_joints <= 23 && K >= 0, PHC_ESHAPE, "%s: num_joints=%d K=%d out of range", fn, num_joints, K);
@@ -277,7 +286,7 @@ extern "C" int phc_amp_obs_smpl(const float* root_pos, const float* root_rot, co
                 "%s: NULL pointer", fn);
     PHC_REQUIRE(obs_stride >= (root_height_obs ? 1 : 0) + 12 + 9 * num_joints + 3 * K, PHC_ESHAPE, "%s: obs_stride too small", fn);
     AmpArgs a{root_pos, root_rot, root_vel, root_ang_vel, dof_pos, dof_vel, key_body_pos, dof_subset, num_joints, K, local_root_obs,
-              root_height_obs, upright, N, obs, obs_stride};
+              root_height_obs, upright, N, obs, obs_stride, ref_device};
     amp_obs_kernel<<<(unsigned)((N + IM_WARPS - 1) / IM_WARPS), IM_WARPS * 32, 0, (cudaStream_t)stream>>>(a);
     return check_launch(fn);
 }
@@ -305,7 +314,7 @@ extern "C" int phc_imitation_reward(phc_view body_pos, phc_view body_rot, phc_vi
 
 extern "C" int phc_im_reset(const int16_t* progress, phc_view rigid_body_pos, phc_view ref_body_pos, const uint8_t* pass_time,
                             int enable_early_termination, const float* termination_distance, int use_mean, int64_t N, int J,
-                            uint8_t* reset, uint8_t* terminated, phc_stream_t stream) {
+                            uint8_t* reset, uint8_t* terminated, int ref_device, phc_stream_t stream) {
     const char* fn = "phc_im_reset";
     PHC_REQUIRE(N >= 0, PHC_EINVAL, "%s: N < 0", fn);
     PHC_REQUIRE(J >= 1 && J <= 32, PHC_ESHAPE, "%s: J=%d outside [1,32]", fn, J);
@@ -313,22 +322,23 @@ extern "C" int phc_im_reset(const int16_t* progress, phc_view rigid_body_pos, ph
     CHECK_VIEW(fn, rigid_body_pos); CHECK_VIEW(fn, ref_body_pos);
     PHC_REQUIRE(progress && pass_time && reset && terminated, PHC_EINVAL, "%s: NULL pointer", fn);
     PHC_REQUIRE(!enable_early_termination || termination_distance, PHC_EINVAL, "%s: termination_distance is NULL", fn);
+    PHC_REQUIRE(ref_device == PHC_REF_DEVICE_CPU || ref_device == PHC_REF_DEVICE_CUDA, PHC_EINVAL, "%s: ref_device must be 0 or 1", fn);
     ResetArgs a{progress, rigid_body_pos, ref_body_pos, pass_time, enable_early_termination, termination_distance, use_mean,
-                N, J, reset, terminated};
+                N, J, reset, terminated, ref_device};
     const unsigned grid = (unsigned)((N + IM_WARPS - 1) / IM_WARPS);
     // (staging the whole record span measured slower -- 27.8 vs 17.2 us: the strided loads touch only the position sectors)
     reset_kernel<false><<<grid, IM_WARPS * 32, 0, (cudaStream_t)stream>>>(a);
     return check_launch(fn);
 }
 
-extern "C" int phc_mpjpe(phc_view body_pos, phc_view ref_body_pos, int64_t N, int J, float* mpjpe, phc_stream_t stream) {
+extern "C" int phc_mpjpe(phc_view body_pos, phc_view ref_body_pos, int64_t N, int J, float* mpjpe, int ref_device, phc_stream_t stream) {
     const char* fn = "phc_mpjpe";
     PHC_REQUIRE(N >= 0, PHC_EINVAL, "%s: N < 0", fn);
     PHC_REQUIRE(J >= 1 && J <= 32, PHC_ESHAPE, "%s: J=%d outside [1,32]", fn, J);
     if (N == 0) return PHC_OK;
     CHECK_VIEW(fn, body_pos); CHECK_VIEW(fn, ref_body_pos);
     PHC_REQUIRE(mpjpe, PHC_EINVAL, "%s: NULL pointer", fn);
-    MpjpeArgs a{body_pos, ref_body_pos, N, J, mpjpe};
+    MpjpeArgs a{body_pos, ref_body_pos, N, J, mpjpe, ref_device};
     mpjpe_kernel<<<(unsigned)((N + IM_WARPS - 1) / IM_WARPS), IM_WARPS * 32, 0, (cudaStream_t)stream>>>(a);
     return check_launch(fn);
 }

@@ -17,6 +17,7 @@ struct StateArgs {
     const float* offset;
     int64_t B;
     phc_motion_state_out o;
+    int dev;
 };
 
 constexpr int MS_WARPS = 4;
@@ -68,13 +69,13 @@ __global__ void __launch_bounds__(MS_WARPS * 32) motion_state_kernel(const State
             if (o.root_ang_vel && j == 0) st3(o.root_ang_vel + q * 3, p);
         }
         if (o.rb_rot || o.root_rot) {
-            Q4 r = slerp_rcp(ldg4a(T.grs + (f0 * NB + j) * 4), ldg4a(T.grs + (f1 * NB + j) * 4), blend);
+            Q4 r = slerp_rcp(ldg4a(T.grs + (f0 * NB + j) * 4), ldg4a(T.grs + (f1 * NB + j) * 4), blend, a.dev);
             if (o.rb_rot) *reinterpret_cast<float4*>(o.rb_rot + (q * NB + j) * 4) = make_float4(r.x, r.y, r.z, r.w);
             if (o.root_rot && j == 0) st4(o.root_rot + q * 4, r);
         }
         if (j >= 1) {
             if (o.dof_pos) {   // motion_lib.py:605-606, 670-673
-                Q4 r = slerp_rcp(ldg4a(T.lrs + (f0 * NB + j) * 4), ldg4a(T.lrs + (f1 * NB + j) * 4), blend);
+                Q4 r = slerp_rcp(ldg4a(T.lrs + (f0 * NB + j) * 4), ldg4a(T.lrs + (f1 * NB + j) * 4), blend, a.dev);
                 st3(o.dof_pos + q * NDOF + (j - 1) * 3, quat_exp_map_fast(r));
             }
             if (o.dof_vel) {
@@ -94,7 +95,7 @@ __global__ void __launch_bounds__(MS_WARPS * 32) motion_state_kernel(const State
 struct ResetArgs2 {
     phc_motion_tables t;
     const int64_t* env_ids; const int64_t* motion_ids; const float* times; const float* offset; int64_t K;
-    float* root_states; float* dof_pos; float* dof_vel; float* body_state; int64_t env_stride;
+    float* root_states; float* dof_pos; float* dof_vel; float* body_state; int64_t env_stride; int dev;
 };
 
 __global__ void __launch_bounds__(MS_WARPS * 32) reset_ref_state_kernel(const ResetArgs2 a) {
@@ -119,7 +120,7 @@ __global__ void __launch_bounds__(MS_WARPS * 32) reset_ref_state_kernel(const Re
         V3 p0 = ldg3(T.gts + (f0 * NB + j) * 3), p1 = ldg3(T.gts + (f1 * NB + j) * 3);
         V3 p{lerp(p0.x, p1.x, one_m, blend), lerp(p0.y, p1.y, one_m, blend), lerp(p0.z, p1.z, one_m, blend)};
         if (a.offset) { p.x = p.x + off.x; p.y = p.y + off.y; p.z = p.z + off.z; }
-        const Q4 r = slerp_rcp(ldg4a(T.grs + (f0 * NB + j) * 4), ldg4a(T.grs + (f1 * NB + j) * 4), blend);
+        const Q4 r = slerp_rcp(ldg4a(T.grs + (f0 * NB + j) * 4), ldg4a(T.grs + (f1 * NB + j) * 4), blend, a.dev);
         V3 v0 = ldg3(T.gvs + (f0 * NB + j) * 3), v1 = ldg3(T.gvs + (f1 * NB + j) * 3);
         const V3 v{lerp(v0.x, v1.x, one_m, blend), lerp(v0.y, v1.y, one_m, blend), lerp(v0.z, v1.z, one_m, blend)};
         V3 w0 = ldg3(T.gavs + (f0 * NB + j) * 3), w1 = ldg3(T.gavs + (f1 * NB + j) * 3);
@@ -135,7 +136,7 @@ __global__ void __launch_bounds__(MS_WARPS * 32) reset_ref_state_kernel(const Re
     }
     if (j >= 1) {
         if (a.dof_pos) {
-            const Q4 r = slerp_rcp(ldg4a(T.lrs + (f0 * NB + j) * 4), ldg4a(T.lrs + (f1 * NB + j) * 4), blend);
+            const Q4 r = slerp_rcp(ldg4a(T.lrs + (f0 * NB + j) * 4), ldg4a(T.lrs + (f1 * NB + j) * 4), blend, a.dev);
             st3(a.dof_pos + e * NDOF + (j - 1) * 3, quat_exp_map_fast(r));
         }
         if (a.dof_vel) {
@@ -151,7 +152,9 @@ __global__ void sample_time_interval_kernel(const float* __restrict__ phase, con
     if (i >= n) return;
     const float fps = (float)(1.0 / 30.0);     // curr_fps = 1/30 as a Python double, cast at the op (motion_lib.py:532)
     const float x = phase[i] * len[i];
-    const float qv = div_mode ? x * (1.0f / fps) : x / fps;
+    // torch-CUDA divides a tensor by a Python scalar as a multiplication by float(1.0 / scalar) with the reciprocal formed in DOUBLE:
+    // 1.0 / (1/30) = 30.000000000000004 -> 30.0f (bit-exact against torch-CUDA on 262144 samples; 1.0f / fps would be 29.999998f)
+    const float qv = div_mode ? x * (float)(1.0 / (1.0 / 30.0)) : x / fps;
     out[i] = (float)(int64_t)qv * fps;
 }
 
@@ -175,7 +178,7 @@ __global__ void pack_frames_kernel(const phc_motion_tables T, float* __restrict_
 using namespace phc;
 
 extern "C" int phc_motion_state(const phc_motion_tables* t, const int64_t* motion_ids, const float* motion_times,
-                                const float* offset, int64_t B, const phc_motion_state_out* out, phc_stream_t stream) {
+                                const float* offset, int64_t B, const phc_motion_state_out* out, int ref_device, phc_stream_t stream) {
     PHC_REQUIRE(t && out, PHC_EINVAL, "phc_motion_state: tables/out is NULL");
     PHC_REQUIRE(B >= 0, PHC_EINVAL, "phc_motion_state: B=%lld < 0", (long long)B);
     if (B == 0) return PHC_OK;
@@ -194,7 +197,8 @@ extern "C" int phc_motion_state(const phc_motion_tables* t, const int64_t* motio
     PHC_REQUIRE(!o.motion_limb_weights || t->limb_weights, PHC_EINVAL, "phc_motion_state: limb_weights table missing");
     PHC_REQUIRE(aligned16(t->grs) && aligned16(t->lrs) && aligned16(o.rb_rot), PHC_EALIGN,
                 "phc_motion_state: grs/lrs tables and rb_rot output must be 16-byte aligned");
-    StateArgs a{*t, motion_ids, motion_times, offset, B, o};
+    PHC_REQUIRE(ref_device == PHC_REF_DEVICE_CPU || ref_device == PHC_REF_DEVICE_CUDA, PHC_EINVAL, "phc_motion_state: ref_device must be 0 or 1");
+    StateArgs a{*t, motion_ids, motion_times, offset, B, o, ref_device};
     const int64_t blocks = (B + MS_WARPS - 1) / MS_WARPS;
     motion_state_kernel<<<(unsigned)blocks, MS_WARPS * 32, 0, (cudaStream_t)stream>>>(a);
     return check_launch("phc_motion_state");
@@ -202,7 +206,8 @@ extern "C" int phc_motion_state(const phc_motion_tables* t, const int64_t* motio
 
 extern "C" int phc_reset_ref_state(const phc_motion_tables* t, const int64_t* env_ids, const int64_t* sampled_motion_ids,
                                    const float* motion_times, const float* global_offset, int64_t K, float* root_states,
-                                   float* dof_pos, float* dof_vel, float* body_state, int64_t env_stride, phc_stream_t stream) {
+                                   float* dof_pos, float* dof_vel, float* body_state, int64_t env_stride, int ref_device,
+                                   phc_stream_t stream) {
     const char* fn = "phc_reset_ref_state";
     PHC_REQUIRE(t, PHC_EINVAL, "%s: tables is NULL", fn);
     PHC_REQUIRE(K >= 0, PHC_EINVAL, "%s: K < 0", fn);
@@ -214,7 +219,8 @@ extern "C" int phc_reset_ref_state(const phc_motion_tables* t, const int64_t* en
     PHC_REQUIRE(!dof_vel || t->dvs, PHC_EINVAL, "%s: dvs table missing", fn);
     PHC_REQUIRE(!body_state || env_stride >= NB * REC, PHC_ESHAPE, "%s: env_stride=%lld < 312", fn, (long long)env_stride);
     PHC_REQUIRE(aligned16(t->grs) && aligned16(t->lrs), PHC_EALIGN, "%s: grs/lrs tables must be 16-byte aligned", fn);
-    ResetArgs2 a{*t, env_ids, sampled_motion_ids, motion_times, global_offset, K, root_states, dof_pos, dof_vel, body_state, env_stride};
+    ResetArgs2 a{*t, env_ids, sampled_motion_ids, motion_times, global_offset, K, root_states, dof_pos, dof_vel, body_state, env_stride,
+                 ref_device};
     reset_ref_state_kernel<<<(unsigned)((K + MS_WARPS - 1) / MS_WARPS), MS_WARPS * 32, 0, (cudaStream_t)stream>>>(a);
     return check_launch(fn);
 }

@@ -12,11 +12,11 @@ struct BodyState { V3 p; Q4 q; V3 v; V3 w; };   // pos, rot (xyzw), lin vel, ang
 PHC_HD void put3(float* o, V3 v) { o[0] = v.x; o[1] = v.y; o[2] = v.z; }
 
 // get_motion_state blend of one body (motion_lib.py:596-610); offset is added to the position only.
-PHC_HD BodyState blend_frames(const BodyState& a, const BodyState& b, float blend, V3 off) {
+PHC_HD BodyState blend_frames(const BodyState& a, const BodyState& b, float blend, V3 off, int dev = PHC_REF_CPU) {
     const float om = 1.0f - blend;
     BodyState r;
     r.p = V3{lerp(a.p.x, b.p.x, om, blend) + off.x, lerp(a.p.y, b.p.y, om, blend) + off.y, lerp(a.p.z, b.p.z, om, blend) + off.z};
-    r.q = slerp_rcp(a.q, b.q, blend);
+    r.q = slerp_rcp(a.q, b.q, blend, dev);
     // velocities feed fp32 outputs only (no index, no flag): one fused multiply-add per component, <= 1 ulp from the reference's
     // (1-b)*x0 + b*x1; the position above keeps the reference's three roundings because the termination test reads it
     r.v = V3{fmaf(blend, b.v.x, om * a.v.x), fmaf(blend, b.v.y, om * a.v.y), fmaf(blend, b.v.z, om * a.v.z)};

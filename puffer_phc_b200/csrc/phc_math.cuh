@@ -7,6 +7,14 @@
 // (host harness); explicit fmaf() is used only where the reference's CPU kernel fuses.
 // Quaternions are xyzw (reference puffer_phc/torch_utils.py:61-62).
 //
+// REFERENCE DEVICE FLAVOUR (`dev` arguments; PHC_REF_CPU = 0, PHC_REF_CUDA = 1).  torch rounds three reductions of this path
+// differently on its two devices (measured on the B200 box with torch 2.11, profiles/r2_torch_device_flavours.md):
+//     torch.sum(q0*q1, -1) over 4      CPU ((p0+p1)+p2)+p3                 CUDA (p0+p2)+(p1+p3)          (slerp, torch_utils.py:113)
+//     torch.norm(d, dim=-1) over 3     CPU sqrt(fma(z,z,fma(y,y,x*x)))     CUDA sqrt((x*x+z*z)+y*y)      (termination test, common.py:343)
+//     .mean(-1) over J                 CPU 8 lanes, tail first, / J        CUDA 16-lane tree * f32(1/J)  (eval variant, common.py:344)
+// They decide flags (termination) and slerp's fall-back branches, and the dot product feeds a cancelling 1-c*c, so every
+// function that contains one takes the flavour to reproduce; everything else is flavour-independent.
+//
 // The header compiles for the host as well (tests/host_math_harness.cpp) so the math can be
 // checked on a CPU-only box before it ever runs on the GPU.
 #pragma once
@@ -25,6 +33,21 @@ struct V3 { float x, y, z; };
 struct Q4 { float x, y, z, w; };
 
 PHC_HD V3 operator-(V3 a, V3 b) { return V3{a.x - b.x, a.y - b.y, a.z - b.z}; }
+
+constexpr int PHC_REF_CPU = 0, PHC_REF_CUDA = 1;
+
+// torch.sum(q0 * q1, dim=-1) (products individually rounded on both devices; only the order of the three additions differs)
+PHC_HD float dot4(Q4 a, Q4 b, int dev) {
+    const float p0 = a.x * b.x, p1 = a.y * b.y, p2 = a.z * b.z, p3 = a.w * b.w;
+    return dev == PHC_REF_CUDA ? (p0 + p2) + (p1 + p3) : ((p0 + p1) + p2) + p3;
+}
+
+// torch.norm over 3 components: CPU sqrt(fma(z,z,fma(y,y,x*x))); CUDA sqrt((x*x + z*z) + y*y) (two reduction lanes: lane 0 takes
+// components 0 and 2, lane 1 component 1, then one shuffle-add) -- both bit-exact against torch on 262144 random triples.
+PHC_HD float norm3(V3 d, int dev = PHC_REF_CPU) {
+    if (dev == PHC_REF_CUDA) return sqrtf((d.x * d.x + d.z * d.z) + d.y * d.y);
+    return sqrtf(fmaf(d.z, d.z, fmaf(d.y, d.y, d.x * d.x)));
+}
 
 // torch.clip(x, 0, 1): NaN propagates (fminf/fmaxf would drop it).
 PHC_HD float clip01(float x) {
@@ -242,8 +265,8 @@ PHC_HD V3 quat_exp_map_fast(Q4 q) {
 // slerp (torch_utils.py:110-131).  The two torch.where fall-backs are evaluated first (they
 // discard the trigonometric result anyway): q0 when |cos| >= 1, the un-normalised midpoint when
 // |sin| < 1e-3.  No renormalisation.
-PHC_HD Q4 slerp(Q4 q0, Q4 q1, float t) {
-    float c = ((q0.x * q1.x + q0.y * q1.y) + q0.z * q1.z) + q0.w * q1.w;
+PHC_HD Q4 slerp(Q4 q0, Q4 q1, float t, int dev = PHC_REF_CPU) {
+    float c = dot4(q0, q1, dev);
     if (c < 0.0f) { q1.x = -q1.x; q1.y = -q1.y; q1.z = -q1.z; q1.w = -q1.w; }
     c = fabsf(c);
     if (c >= 1.0f) return q0;
@@ -259,8 +282,8 @@ PHC_HD Q4 slerp(Q4 q0, Q4 q1, float t) {
 // Same slerp for the fused step: identical branch decisions (they depend on c and s only), but one IEEE
 // reciprocal shared by the two ratios instead of two divisions, and a bounded-range polynomial sine
 // (the arguments lie in [0, pi/2]); a few ulp from slerp().
-PHC_HD Q4 slerp_rcp(Q4 q0, Q4 q1, float t) {
-    float c = ((q0.x * q1.x + q0.y * q1.y) + q0.z * q1.z) + q0.w * q1.w;
+PHC_HD Q4 slerp_rcp(Q4 q0, Q4 q1, float t, int dev = PHC_REF_CPU) {
+    float c = dot4(q0, q1, dev);
     if (c < 0.0f) { q1.x = -q1.x; q1.y = -q1.y; q1.z = -q1.z; q1.w = -q1.w; }
     c = fabsf(c);
     if (c >= 1.0f) return q0;
@@ -278,13 +301,13 @@ PHC_HD Q4 slerp_rcp(Q4 q0, Q4 q1, float t) {
 
 // exp_map_to_quat (torch_utils.py:333-365) = quat_from_angle_axis(exp_map_to_angle_axis(e)); norms use the CPU reference's
 // fma chain, the small-angle mask falls back to angle 0 about (0,0,1).
-PHC_HD Q4 exp_map_to_quat(V3 e) {
-    float angle = sqrtf(fmaf(e.z, e.z, fmaf(e.y, e.y, e.x * e.x)));
+PHC_HD Q4 exp_map_to_quat(V3 e, int dev = PHC_REF_CPU) {
+    float angle = norm3(e, dev);
     V3 axis{e.x / angle, e.y / angle, e.z / angle};
     angle = atan2f(sinf(angle), cosf(angle));                       // normalize_angle (:50-51)
     if (!(fabsf(angle) > 1e-5f)) { angle = 0.0f; axis = V3{0.0f, 0.0f, 1.0f}; }
     const float th = angle / 2.0f;
-    float an = sqrtf(fmaf(axis.z, axis.z, fmaf(axis.y, axis.y, axis.x * axis.x)));
+    float an = norm3(axis, dev);
     if (an < 1e-9f) an = 1e-9f;
     const float sn = sinf(th);
     const float x = (axis.x / an) * sn, y = (axis.y / an) * sn, z = (axis.z / an) * sn, w = cosf(th);
@@ -296,8 +319,31 @@ PHC_HD Q4 exp_map_to_quat(V3 e) {
 // lerp as written in get_motion_state (motion_lib.py:596-603): (1-b)*x0 + b*x1
 PHC_HD float lerp(float a, float b, float one_m, float t) { return one_m * a + t * b; }
 
-// torch.norm over 3 components on the CPU reference: sqrt(fma(z,z,fma(y,y,x*x))).
-PHC_HD float norm3(V3 d) { return sqrtf(fmaf(d.z, d.z, fmaf(d.y, d.y, d.x * d.x))); }
+// .mean(dim=-1) over n <= 32 contiguous values in torch's own summation order (both fitted bit-exactly, n = 20 and 24):
+//   CUDA: the reduce kernel runs bx = last_pow2(n) lanes, lane k first adds v[k + bx] (when it exists), then a shuffle tree (offsets
+//         bx/2 .. 1), and the sum is MULTIPLIED by float(1/n);
+//   CPU:  eight vector lanes a_k = v[k] + v[k+8] + ... over the full rows of 8, the scalar tail (n % 8 elements) summed first, then
+//         the lanes added one by one, and the sum is DIVIDED by n.
+PHC_HD float mean_ordered(const float* v, int n, int dev) {
+    if (dev == PHC_REF_CUDA) {
+        int bx = 1;
+        while (bx * 2 <= n) bx *= 2;
+        float s[32];
+        for (int k = 0; k < bx; ++k) s[k] = (k + bx < n) ? v[k] + v[k + bx] : v[k];
+        for (int off = bx / 2; off >= 1; off /= 2)
+            for (int k = 0; k < off; ++k) s[k] = s[k] + s[k + off];
+        return s[0] * (1.0f / (float)n);
+    }
+    const int full = (n / 8) * 8;
+    float s = 0.0f;
+    for (int i = full; i < n; ++i) s = (i == full) ? v[i] : s + v[i];
+    for (int k = 0; k < 8 && k < full; ++k) {
+        float a = v[k];
+        for (int i = k + 8; i < full; i += 8) a = a + v[i];
+        s = (k == 0 && full == n) ? a : s + a;
+    }
+    return s / (float)n;
+}
 
 // mean over xyz of squares: ((x^2 + y^2) + z^2) / 3  ((diff**2).mean(dim=-1), common.py:300)
 PHC_HD float mean_sq3(V3 d) { return ((d.x * d.x + d.y * d.y) + d.z * d.z) / 3.0f; }

@@ -364,7 +364,7 @@ __global__ void __maxnreg__(ST_MAXREG) step_fused_kernel(const StepArgs a) {   /
                 body = BodyState{ld3(sj), ld4(sj + 3), ld3(sj + 7), ld3(sj + 10)};
                 const BodyState F0 = read_frame(wbuf + FRAME_F, j);
                 const BodyState F1 = (cur.f1 == cur.f0) ? F0 : read_frame(wbuf + 2 * FRAME_F, j);
-                ref = blend_frames(F0, F1, cur.blend, V3{cur.offx, cur.offy, cur.offz});
+                ref = blend_frames(F0, F1, cur.blend, V3{cur.offx, cur.offy, cur.offz}, cfg.ref_device);
                 if (role == 0 && in.dof_force && j < 23) {                         // humanoid_phc.py:1295-1303
                     const float* df = wbuf + 3 * FRAME_F + 3 * j;
                     power = (fabsf(df[0] * df[72]) + fabsf(df[1] * df[73])) + fabsf(df[2] * df[74]);
@@ -407,7 +407,7 @@ __global__ void __maxnreg__(ST_MAXREG) step_fused_kernel(const StepArgs a) {   /
                     float sp, sr, sv, sa, dist = 0.0f;
                     reward_terms_body_fma(body, ref, sp, sr, sv, sa);
                     if ((cfg.reset_body_mask >> j) & 1u) {
-                        dist = norm3(body.p - ref.p);
+                        dist = norm3(body.p - ref.p, cfg.ref_device);
                         if (!cfg.use_mean) dist = (dist > __ldg(in.term_dist + j)) ? 1.0f : 0.0f;     // common.py:347-350 (any)
                     }
                     *reinterpret_cast<float4*>(rj) = make_float4(sp, sr, sv, sa);
@@ -450,7 +450,13 @@ __global__ void __maxnreg__(ST_MAXREG) step_fused_kernel(const StepArgs a) {   /
                     if (cfg.enable_early_termination) {
                         if (cfg.use_mean) {                                               // common.py:342-346
                             const int first = __ffs(cfg.reset_body_mask) - 1;
-                            fallen = (t4 / (float)__popc(cfg.reset_body_mask & 0xffffffu)) > __ldg(in.term_dist + first);
+                            // torch's own summation order over the body subset (eval mode only; the per-body distances are still in smem)
+                            float dsub[NB];
+                            int n = 0;
+                            for (int b2 = 0; b2 < NB; ++b2)
+                                if ((cfg.reset_body_mask >> b2) & 1u) dsub[n++] = red[(slot * NB + b2) * 8 + 4];
+                            const float mean = mean_ordered(dsub, n, cfg.ref_device);
+                            fallen = mean > __ldg(in.term_dist + first);
                         } else {
                             fallen = t4 > 0.0f;
                         }
@@ -649,6 +655,7 @@ extern "C" int phc_step_fused(const phc_motion_tables* t, const phc_step_in* in,
     PHC_REQUIRE(out->raw_stride >= (in->dof_force ? 5 : 4), PHC_ESHAPE, "%s: raw_stride=%lld too small", fn, (long long)out->raw_stride);
     PHC_REQUIRE(!out->obs_norm || (in->rms_mean && in->rms_var), PHC_EINVAL, "%s: obs_norm needs rms_mean and rms_var", fn);
     PHC_REQUIRE((cfg->reset_body_mask & 0xffffffu) != 0 || !cfg->enable_early_termination, PHC_EINVAL, "%s: empty reset_body_mask", fn);
+    PHC_REQUIRE(cfg->ref_device == PHC_REF_DEVICE_CPU || cfg->ref_device == PHC_REF_DEVICE_CUDA, PHC_EINVAL, "%s: ref_device must be 0 (torch CPU) or 1 (torch CUDA)", fn);
     PHC_REQUIRE(t->motion_len && t->motion_dt && t->num_frames && t->length_starts, PHC_EINVAL, "%s: per-motion tables missing", fn);
     const bool packed = t->packed != nullptr;
     if (packed) {

@@ -107,7 +107,7 @@ def build_amp_observations_smpl(root_pos, root_rot, root_vel, root_ang_vel, dof_
     with torch.cuda.device(obs.device):
         _ffi.check(lib.phc_amp_obs_smpl(*[_ffi.ptr(t) for t in ts], _ffi.ptr(sub), nj, K, int(bool(local_root_obs)),
                                         int(bool(root_height_obs)), int(bool(upright)), B, _ffi.ptr(obs), obs.stride(0),
-                                        _ffi.stream_ptr()), "build_amp_observations_smpl")
+                                        _ffi.ref_device(), _ffi.stream_ptr()), "build_amp_observations_smpl")
     col = W
     for x in extra:
         obs[:, col:col + x.shape[-1]] = x
@@ -148,7 +148,8 @@ def compute_humanoid_im_reset(reset_buf, progress_buf, contact_buf, contact_body
     term = torch.empty(B, dtype=torch.bool, device=pos.device)
     with torch.cuda.device(pos.device):
         _ffi.check(lib.phc_im_reset(_ffi.ptr(prog), _ffi.view3(pos), _ffi.view3(ref), _ffi.ptr(pt), int(bool(enable_early_termination)),
-                                    _ffi.ptr(td), int(bool(use_mean)), B, J, _ffi.ptr(reset), _ffi.ptr(term), _ffi.stream_ptr()),
+                                    _ffi.ptr(td), int(bool(use_mean)), B, J, _ffi.ptr(reset), _ffi.ptr(term), _ffi.ref_device(),
+                                    _ffi.stream_ptr()),
                    "compute_humanoid_im_reset")
     if reset_buf.dtype != torch.bool:
         reset, term = reset.to(reset_buf.dtype), term.to(reset_buf.dtype)
@@ -163,5 +164,6 @@ def compute_mpjpe(rigid_body_pos, ref_body_pos):
     B, J = pos.shape[0], pos.shape[1]
     out = torch.empty(B, dtype=torch.float32, device=pos.device)
     with torch.cuda.device(pos.device):
-        _ffi.check(lib.phc_mpjpe(_ffi.view3(pos), _ffi.view3(ref), B, J, _ffi.ptr(out), _ffi.stream_ptr()), "compute_mpjpe")
+        _ffi.check(lib.phc_mpjpe(_ffi.view3(pos), _ffi.view3(ref), B, J, _ffi.ptr(out), _ffi.ref_device(), _ffi.stream_ptr()),
+                   "compute_mpjpe")
     return out

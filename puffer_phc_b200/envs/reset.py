@@ -66,7 +66,7 @@ def reset_envs(env: EnvTensors, motion_lib, env_ids: torch.Tensor, random_start:
         _ffi.check(lib.phc_reset_ref_state(C.byref(motion_lib.ctables), _ffi.ptr(env_ids), _ffi.ptr(env.sampled_motion_ids),
                                            _ffi.ptr(motion_times), _ffi.ptr(env.global_offset), env_ids.shape[0],
                                            _ffi.ptr(env.humanoid_root_states), _ffi.ptr(env.dof_pos), _ffi.ptr(env.dof_vel), _ffi.ptr(bs),
-                                           bs.stride(0), _ffi.stream_ptr()), "phc_reset_ref_state")
+                                           bs.stride(0), _ffi.ref_device(), _ffi.stream_ptr()), "phc_reset_ref_state")
     # _reset_ref_state_init tail (:721-727) and _reset_env_tensors (:774-777)
     env.global_offset[env_ids] = 0
     env.motion_start_times[env_ids] = motion_times

@@ -43,6 +43,8 @@ class StepConfig:
     termination_distance: float = 0.25          # config.py:85
     reset_bodies: Sequence[int] = field(default_factory=lambda: tuple(range(24)))
     use_mean: bool = False                      # flag_im_eval (humanoid_phc.py:1332)
+    ref_device: Optional[str] = None            # "cuda" / "cpu": whose torch rounding the flag-deciding reductions reproduce
+                                                # (include/phc_b200.h PHC_REF_DEVICE_*); None = the package setting (default cuda)
 
     def eval_mode(self) -> "StepConfig":
         """toggle_eval_mode (humanoid_phc.py:1421-1438): 0.5 m, mean over the 20 eval bodies."""
@@ -93,7 +95,8 @@ class FusedStep:
             float(torch.tensor(c.dt, dtype=torch.float32)),
             (C.c_float * 4)(c.k_pos, c.k_rot, c.k_vel, c.k_ang_vel), (C.c_float * 4)(c.w_pos, c.w_rot, c.w_vel, c.w_ang_vel),
             float(c.rew_power_coef), mask, int(c.enable_early_termination), int(c.use_mean),
-            float(rms.epsilon) if rms is not None else 1e-5, float(rms.clip) if rms is not None else 10.0)
+            float(rms.epsilon) if rms is not None else 1e-5, float(rms.clip) if rms is not None else 10.0,
+            _ffi.ref_device(c.ref_device))
 
     def set_termination_distances(self, d) -> None:           # humanoid_phc.py:1336-1337
         self.termination_distances[:] = d

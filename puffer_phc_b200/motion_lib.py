@@ -347,9 +347,10 @@ class MotionLibBase:
             motion_len -= truncate_time
         return phase * motion_len
 
-    def sample_time_interval(self, motion_ids, truncate_time=None, cpu_division: bool = False):
-        """motion_lib.py:526-535.  ``cpu_division`` selects the reference's CPU rounding (true division);
-        the default reproduces what the reference computes when it runs on CUDA (scalar reciprocal multiply)."""
+    def sample_time_interval(self, motion_ids, truncate_time=None, cpu_division=None):
+        """motion_lib.py:526-535.  ``cpu_division=True`` selects the reference's CPU rounding (true division), ``False`` what
+        the reference computes when it runs on CUDA (multiplication by float(1.0 / (1/30)) = 30.0f); ``None`` follows the package's
+        reference-device setting (``puffer_phc_b200.set_reference_device``, default CUDA)."""
         phase = torch.rand(motion_ids.shape, device=self._device)
         motion_len = self._motion_lengths[motion_ids]
         if truncate_time is not None:
@@ -357,8 +358,10 @@ class MotionLibBase:
             motion_len -= truncate_time
         return self.time_interval_from_phase(phase, motion_len, cpu_division)
 
-    def time_interval_from_phase(self, phase, motion_len, cpu_division: bool = False):
+    def time_interval_from_phase(self, phase, motion_len, cpu_division=None):
         _ffi.require_cuda(phase, motion_len)
+        if cpu_division is None:
+            cpu_division = _ffi.ref_device() == _ffi.REF_CPU
         phase, motion_len = phase.contiguous().float(), motion_len.contiguous().float()
         out = torch.empty_like(phase)
         with torch.cuda.device(self._device):
@@ -387,7 +390,7 @@ class MotionLibBase:
                                  *[(dbg[k].data_ptr() if k in dbg else None) for k in _ffi.STATE_FIELDS[13:]])
         with torch.cuda.device(self._device):
             _ffi.check(self._lib.phc_motion_state(C.byref(self._ctables), _ffi.ptr(ids), _ffi.ptr(times), _ffi.ptr(off), B,
-                                                  C.byref(so), _ffi.stream_ptr()), "phc_motion_state")
+                                                  C.byref(so), _ffi.ref_device(), _ffi.stream_ptr()), "phc_motion_state")
         out.update(dbg)
         return out
 

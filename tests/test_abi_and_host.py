@@ -29,7 +29,7 @@ def test_library_exports_every_declared_symbol():
     out = subprocess.check_output(["nm", "-D", "--defined-only", _ffi.library_path()], text=True)
     exported = set(re.findall(r"\bT (phc_[a-z0-9_]+)", out))
     assert set(declared) <= exported
-    assert lib.phc_version() == 100
+    assert lib.phc_version() == 110
 
 
 def test_library_contains_sm100a_code():
@@ -75,7 +75,7 @@ def test_argument_validation_without_gpu():
     assert lib.phc_rms_forward(None, 934, None, None, 1e-5, 10.0, 4, 934, None, 934, None) == _ffi.PHC_EINVAL
     assert lib.phc_rms_forward(C.c_void_p(16), 10, C.c_void_p(16), C.c_void_p(16), 1e-5, 10.0, 4, 934, C.c_void_p(16), 934, None) == _ffi.PHC_ESHAPE
     assert lib.phc_step_fused(None, None, None, None, None) == _ffi.PHC_EINVAL
-    assert lib.phc_motion_state(None, None, None, None, 3, None, None) == _ffi.PHC_EINVAL
+    assert lib.phc_motion_state(None, None, None, None, 3, None, 0, None) == _ffi.PHC_EINVAL
     with pytest.raises(ValueError):
         _ffi.check(_ffi.PHC_EINVAL, "x")
     with pytest.raises(NotImplementedError):

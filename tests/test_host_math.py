@@ -48,7 +48,7 @@ def _run(harness, T, S, term, mask, use_mean, power):
     sin = _ffi.StepIn(_p(arrs["bs"]), bs.shape[1], _p(arrs["prog"]), _p(arrs["st"]), _p(arrs["so"]), _p(arrs["ids"]), _p(arrs["go"]),
                       _p(arrs["df"]) if power else None, _p(arrs["dv"]) if power else None, _p(arrs["td"]), None, None, N)
     cfg = _ffi.StepCfg(float(np.float32(1.0 / 30.0)), (C.c_float * 4)(*K), (C.c_float * 4)(*W), float(np.float32(0.0005)),
-                       mask, 1, int(use_mean), 1e-5, 10.0)
+                       mask, 1, int(use_mean), 1e-5, 10.0, 0)
     rw = 5 if power else 4
     obs, rew, raw = np.zeros((N, 934), np.float32), np.zeros(N, np.float32), np.zeros((N, rw), np.float32)
     rs, tm = np.zeros(N, np.uint8), np.zeros(N, np.uint8)
