@@ -306,7 +306,25 @@ typedef struct phc_step_out {
                                     buffer once, step a whole rollout, reduce once                         */
     float *ref_state_t;          /* optional debug [N,312]: blended reference pos72|rot96|vel72|ang72 at t */
     float *ref_state_t1;         /* optional debug [N,312] at t+1                                          */
+    double *metric_partials;     /* optional [phc_step_num_partials(), PHC_NUM_METRICS] fp64: per-CTA sums of the step's episode
+                                    metrics PHC_M_STEPS .. PHC_M_TERMINATIONS (same overwrite / accumulate rule as
+                                    moment_partials); fold with phc_stats_reduce()                         */
 } phc_step_out;
+
+/* Episode metrics the reference logs (puffer_phc/clean_pufferl/env.py:102-110, 118-131, 139-164): sums, so that ranks can be
+ * all-reduced and means formed afterwards.  phc_step_fused fills 0..8, phc_auto_reset 9..12 (and 0..8 when asked to). */
+#define PHC_NUM_METRICS 16
+enum {
+    PHC_M_STEPS = 0,        /* env-steps counted                                                        */
+    PHC_M_REWARD = 1,       /* sum rew_buf                                                              */
+    PHC_M_RAW0 = 2,         /* sum reward_raw[:, 0..4]: r_pos, r_rot, r_vel, r_ang_vel, power  (2..6)   */
+    PHC_M_RESETS = 7,       /* sum reset_buf                                                            */
+    PHC_M_TERMINATIONS = 8, /* sum _terminate_buf                                                       */
+    PHC_M_TRUNCATIONS = 9,  /* resets that are not terminations (env.py:128-131)                        */
+    PHC_M_EP_RETURN = 10,   /* sum of the finished episodes' returns (env.py:118)                       */
+    PHC_M_EP_LENGTH = 11,   /* sum of the finished episodes' lengths (env.py:119)                       */
+    PHC_M_EPISODES = 12     /* finished episodes (env.py:117)                                           */
+};
 
 /* number of [2,934] fp64 partial slots phc_step_fused writes (a function of the device only) */
 int phc_step_num_partials(void);

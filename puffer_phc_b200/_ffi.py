@@ -24,6 +24,9 @@ EXPORTS = (
 )
 
 VERSION = 110
+NUM_METRICS = 16
+METRIC_NAMES = ("steps", "reward", "r_pos", "r_rot", "r_vel", "r_ang_vel", "r_power", "resets", "terminations", "truncations",
+                "episode_return", "episode_length", "episodes")
 REF_CPU, REF_CUDA = 0, 1
 PHC_OK, PHC_EINVAL, PHC_EALIGN, PHC_ESHAPE, PHC_EUNSUPPORTED = 0, -1, -2, -3, -4
 
@@ -70,6 +73,7 @@ class StepOut(C.Structure):
         ("obs", C.c_void_p), ("obs_stride", C.c_int64), ("obs_norm", C.c_void_p), ("reward", C.c_void_p),
         ("reward_raw", C.c_void_p), ("raw_stride", C.c_int64), ("reset", C.c_void_p), ("terminated", C.c_void_p),
         ("moment_partials", C.c_void_p), ("accumulate_partials", C.c_int), ("ref_state_t", C.c_void_p), ("ref_state_t1", C.c_void_p),
+        ("metric_partials", C.c_void_p),
     ]
 
 

@@ -303,7 +303,8 @@ __global__ void __maxnreg__(ST_MAXREG) step_fused_kernel(const StepArgs a) {   /
     float* wbufs = tiles + ST_TILES * ST_ENVS * OBS_W;                       // [2][S][record | frame 0 | frame 1 | dof]
     float* red = wbufs + ST_NBUF * ST_WBUF_F;                                // [S][24][8]  per-body partials (role A)
     float* red2 = red + ST_ENVS * NB * 8;                                    // [S][6][4]   second-stage partial sums
-    EnvPlan* plans = reinterpret_cast<EnvPlan*>(red2 + ST_ENVS * 24);        // [ST_PLANS][2S]
+    float* macc = red2 + ST_ENVS * 24;                                       // [S][12]     per-slot metric sums of this launch (role A leaders)
+    EnvPlan* plans = reinterpret_cast<EnvPlan*>(macc + ST_ENVS * 12);        // [ST_PLANS][2S]
     uint64_t* bars = reinterpret_cast<uint64_t*>(plans + ST_PLANS * ST_NBUF);
     uint64_t* full = bars;                    // [ST_TILES] tile b written by all compute warps
     uint64_t* empty = bars + ST_TILES;        // [ST_TILES] tile b drained by the writers
@@ -339,6 +340,10 @@ __global__ void __maxnreg__(ST_MAXREG) step_fused_kernel(const StepArgs a) {   /
             if (cur.valid) issue_env<PACKED>(a, cur, (int64_t)blockIdx.x * ST_ENVS + slot, role, wbuf, j, &lfull[buf]);
         }
         cp_async_commit();
+        if (role == 0 && j == 0) {         // the leader lane of a slot owns that slot's metric sums for the whole launch
+#pragma unroll
+            for (int k = 0; k < 12; ++k) macc[slot * 12 + k] = 0.0f;
+        }
         int it = 0;
         PROF_DECL
         for (int64_t blk = blockIdx.x; blk < a.num_blocks; blk += gridDim.x, ++it) {
@@ -471,9 +476,17 @@ __global__ void __maxnreg__(ST_MAXREG) step_fused_kernel(const StepArgs a) {   /
                         rew = rew + pr;
                         rr[4] = pr;
                     }
+                    const bool rst = (cur.t >= cur.mlen) || fallen;                       // humanoid_phc.py:1315, common.py:362
                     out.reward[e] = rew;
                     out.terminated[e] = fallen ? 1 : 0;
-                    out.reset[e] = (cur.t >= cur.mlen) ? 1 : (fallen ? 1 : 0);            // humanoid_phc.py:1315, common.py:362
+                    out.reset[e] = rst ? 1 : 0;
+                    if (out.metric_partials) {       // episode metrics (clean_pufferl/env.py:102-110): sums kept in shared memory, no registers
+                        float* m = macc + slot * 12;
+                        m[0] += 1.0f; m[1] += rew; m[2] += r0; m[3] += r1; m[4] += r2; m[5] += r3;
+                        if (in.dof_force) m[6] += rr[4];
+                        if (rst) m[7] += 1.0f;
+                        if (fallen) m[8] += 1.0f;
+                    }
                 }
             } else if (valid) {
                 // ============ role B: every observation block (task obs against the reference at t+1, self obs) ===========
@@ -498,6 +511,16 @@ __global__ void __maxnreg__(ST_MAXREG) step_fused_kernel(const StepArgs a) {   /
         if (lane == 0) for (int k = 0; k < 5; ++k) g_prof[blockIdx.x][warp][k] = prof_t[k];
 #endif
         cp_async_wait_all();
+        if (role == 0 && out.metric_partials) {      // fold the slots' sums in a fixed order into this CTA's fp64 metric slot (deterministic)
+            asm volatile("bar.sync 8, %0;" ::"n"(3 * ST_GROUPS * 32) : "memory");
+            if (warp == 0 && lane < 9) {
+                float sum = 0.0f;
+#pragma unroll
+                for (int sl = 0; sl < ST_ENVS; ++sl) sum = sum + macc[sl * 12 + lane];
+                double* mp = out.metric_partials + (int64_t)blockIdx.x * PHC_NUM_METRICS + lane;
+                *mp = (out.accumulate_partials ? *mp : 0.0) + (double)sum;
+            }
+        }
     } else if (warp < ST_CWARPS + ST_WWARPS) {
         // ====================================== writer warps =======================================
         const int wtid = tid - ST_CWARPS * 32;
@@ -628,7 +651,7 @@ __global__ void __maxnreg__(ST_MAXREG) step_fused_kernel(const StepArgs a) {   /
     }
 }
 
-constexpr size_t ST_SMEM = (size_t)(ST_TILES * ST_ENVS * OBS_W + ST_NBUF * ST_WBUF_F + ST_ENVS * NB * 8 + ST_ENVS * 24) * sizeof(float) +
+constexpr size_t ST_SMEM = (size_t)(ST_TILES * ST_ENVS * OBS_W + ST_NBUF * ST_WBUF_F + ST_ENVS * NB * 8 + ST_ENVS * 24 + ST_ENVS * 12) * sizeof(float) +
                            ST_PLANS * ST_NBUF * sizeof(EnvPlan) +
                            (2 * ST_TILES + ST_PLANS + ST_NBUF) * sizeof(uint64_t);
 static_assert(sizeof(EnvPlan) == 48, "plan record layout");
