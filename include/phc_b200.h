@@ -333,6 +333,75 @@ int phc_step_fused(const phc_motion_tables *t, const phc_step_in *in, const phc_
                    const phc_step_out *out, phc_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------- */
+/* Auto-reset after the step ("next" row f1), on the device, no host synchronisation:           */
+/* PHCPufferEnv.step bookkeeping (puffer_phc/clean_pufferl/env.py:102-140) + HumanoidPHC.reset  */
+/* of the flagged envs = _reset_envs (puffer_phc/envs/humanoid_phc.py:663-674):                 */
+/* _sample_ref_state (:843-873) + _set_env_state (:899-929) + the per-env scalars (:721-727,    */
+/* :774-777) + _compute_observations(env_ids) (:935-959).  Replaces torch.nonzero (a host sync),*/
+/* ~20 indexed assignments, a subset get_motion_state x2 and the subset observation functions.  */
+/* Two kernel launches, CUDA-graph capturable together with phc_step_fused.                     */
+/* ------------------------------------------------------------------------------------------- */
+typedef struct phc_reset_env {   /* the per-env tensors HumanoidPHC owns (humanoid_phc.py:523-598); flagged rows are rewritten in place */
+    float *body_state;           /* PhysX rigid-body tensor AoS [N, env_stride]: _rigid_body_pos/rot/vel/ang_vel of the flagged envs */
+    int64_t env_stride;          /* >= 312 */
+    float *root_states;          /* optional [N,13] _humanoid_root_states                                  */
+    float *dof_pos, *dof_vel;    /* optional [N,69] _dof_pos / _dof_vel                                    */
+    int16_t *progress;           /* [N] progress_buf      -> 0                                             */
+    float *start_time;           /* [N] _motion_start_times -> the sampled start time                      */
+    float *start_offset;         /* [N] _motion_start_times_offset -> 0                                    */
+    float *global_offset;        /* [N,3] _global_offset: READ by the state query, then -> 0 (:721)        */
+    const int64_t *motion_ids;   /* [N] _sampled_motion_ids (unchanged by a reset)                         */
+    uint8_t *reset, *terminated; /* [N] reset_buf / _terminate_buf: in = this step's flags, cleared for the flagged envs */
+    float *obs;                  /* [N, obs_stride >= 934] obs_buf: rows of the flagged envs recomputed    */
+    int64_t obs_stride;
+    float *obs_norm;             /* optional [N, obs_stride]: the RunningNorm-normalised copy of those rows */
+    const float *rms_mean, *rms_var; /* device [934], needed iff obs_norm                                   */
+} phc_reset_env;
+
+typedef struct phc_reset_book {  /* PHCPufferEnv.step bookkeeping (clean_pufferl/env.py:102-140); every pointer may be NULL */
+    const float *rewards;        /* [N] rew_buf of this step                                               */
+    const float *reward_raw;     /* [N, raw_stride] extras["reward_raw"]                                   */
+    int64_t raw_stride;
+    int raw_dim;                 /* 4 or 5                                                                 */
+    uint8_t *terminals, *truncations, *masks;   /* [N] out (env.py:111-133)                                */
+    float *episode_returns;      /* [N] in/out (env.py:118-120, 139)                                       */
+    int32_t *episode_lengths;    /* [N] in/out (env.py:119-121, 140)                                       */
+    double *metrics;             /* [PHC_NUM_METRICS] device accumulators, += : always PHC_M_TRUNCATIONS .. PHC_M_EPISODES;
+                                    PHC_M_STEPS .. PHC_M_TERMINATIONS only when step_metrics (otherwise phc_step_fused sums them) */
+    int step_metrics;
+} phc_reset_book;
+
+typedef struct phc_reset_cfg {
+    float dt;                    /* float32(isaac dt)                                                      */
+    int state_init;              /* 0 = StateInit.Random / Hybrid-ref: start = sample_time_interval (motion_lib.py:526-535);
+                                    1 = StateInit.Start: start = 0 (humanoid_phc.py:846-851)               */
+    int flag_test;               /* motion_times[:] = 0 (humanoid_phc.py:853-854)                          */
+    int ref_device;              /* PHC_REF_DEVICE_*                                                       */
+    float rms_eps, rms_clip;
+} phc_reset_cfg;
+
+/* phase: device [N] uniforms drawn by the caller with torch.rand (the RNG stays torch's): the k-th flagged env in ascending env
+ * order consumes phase[k], as the reference's torch.rand(len(env_ids)) assigns them.  reset_ids (optional, [N] int64) receives the
+ * flagged env ids in ascending order, reset_count (optional, device int32) their number -- nothing is read back by the library.
+ * scratch: >= phc_auto_reset_scratch_bytes(N) bytes, 8-byte aligned.
+ * moment_partials (optional, [phc_auto_reset_num_partials(), 2, 934] fp64, ADDED to) and row_adjust (optional, device double, -=
+ * truncated rows): the correction that turns column moments accumulated by phc_step_fused over the PRE-reset observations into
+ * moments over the rows the reference stores (post-reset row for a terminated env, no row for a truncated env: clean_pufferl/
+ * env.py:132-133, structs.py:116); fold both with phc_stats_reduce(). */
+int phc_auto_reset_num_partials(void);
+int64_t phc_auto_reset_scratch_bytes(int64_t N);
+int phc_auto_reset(const phc_motion_tables *t, const phc_reset_env *env, const phc_reset_book *book, const phc_reset_cfg *cfg,
+                   const float *phase, int64_t N, int64_t *reset_ids, int32_t *reset_count, void *scratch,
+                   double *moment_partials, double *row_adjust, phc_stream_t stream);
+
+/* Fold per-CTA partials into the rank's statistics buffer stats = [n, sum x (C), sum x^2 (C), metrics (PHC_NUM_METRICS)] -- the ONE
+ * buffer that is all-reduced across ranks (RunningNorm moments + episode metrics):
+ *   stats[0] += rows (+ *row_adjust); stats[1 + i] += sum_p moment_partials[p][i]; stats[1 + 2C + k] += sum_p metric_partials[p][k]
+ * in a fixed order (deterministic).  zero_partials: every partial read (and *row_adjust) is cleared in the same launch. */
+int phc_stats_reduce(double *moment_partials, int num_partials, int C, int64_t rows, double *row_adjust,
+                     double *metric_partials, int num_metric_partials, double *stats, int zero_partials, phc_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------- */
 /* RunningNorm (puffer_phc/policies/running_norm.py:5-53)                                       */
 /* ------------------------------------------------------------------------------------------- */
 

@@ -20,7 +20,8 @@ EXPORTS = (
     "phc_version", "phc_last_error", "phc_pack_frames", "phc_motion_state", "phc_reset_ref_state", "phc_sample_time_interval",
     "phc_imitation_obs_v6", "phc_self_obs_smpl_max", "phc_amp_obs_smpl", "phc_imitation_reward", "phc_im_reset",
     "phc_step_num_partials", "phc_step_fused", "phc_rms_forward", "phc_rms_scratch_doubles", "phc_rms_moments",
-    "phc_rms_reduce_partials", "phc_rms_finalize", "phc_gae", "phc_build_motion_tables", "phc_build_motion_aa", "phc_cast_f64_f32", "phc_mpjpe", "phc_frame_blend",
+    "phc_rms_reduce_partials", "phc_rms_finalize", "phc_auto_reset_num_partials", "phc_auto_reset_scratch_bytes", "phc_auto_reset",
+    "phc_stats_reduce", "phc_gae", "phc_build_motion_tables", "phc_build_motion_aa", "phc_cast_f64_f32", "phc_mpjpe", "phc_frame_blend",
 )
 
 VERSION = 110
@@ -77,6 +78,24 @@ class StepOut(C.Structure):
     ]
 
 
+class ResetEnv(C.Structure):
+    _fields_ = [("body_state", C.c_void_p), ("env_stride", C.c_int64), ("root_states", C.c_void_p), ("dof_pos", C.c_void_p),
+                ("dof_vel", C.c_void_p), ("progress", C.c_void_p), ("start_time", C.c_void_p), ("start_offset", C.c_void_p),
+                ("global_offset", C.c_void_p), ("motion_ids", C.c_void_p), ("reset", C.c_void_p), ("terminated", C.c_void_p),
+                ("obs", C.c_void_p), ("obs_stride", C.c_int64), ("obs_norm", C.c_void_p), ("rms_mean", C.c_void_p), ("rms_var", C.c_void_p)]
+
+
+class ResetBook(C.Structure):
+    _fields_ = [("rewards", C.c_void_p), ("reward_raw", C.c_void_p), ("raw_stride", C.c_int64), ("raw_dim", C.c_int),
+                ("terminals", C.c_void_p), ("truncations", C.c_void_p), ("masks", C.c_void_p), ("episode_returns", C.c_void_p),
+                ("episode_lengths", C.c_void_p), ("metrics", C.c_void_p), ("step_metrics", C.c_int)]
+
+
+class ResetCfg(C.Structure):
+    _fields_ = [("dt", C.c_float), ("state_init", C.c_int), ("flag_test", C.c_int), ("ref_device", C.c_int), ("rms_eps", C.c_float),
+                ("rms_clip", C.c_float)]
+
+
 class BuildIn(C.Structure):
     """phc_build_in (raw clips -> tables, row f4)."""
     _fields_ = [(k, C.c_void_p) for k in ("pose_quat_global", "root_trans", "in_start", "num_frames", "out_start", "fps",
@@ -112,6 +131,11 @@ def _declare(lib):
     lib.phc_rms_reduce_partials.argtypes = [P, I, I64, I, P, P]
     lib.phc_rms_finalize.argtypes = [P, I, P, P, P, P]
     lib.phc_gae.argtypes = [P, P, P, I64, F, F, P, I, P]
+    lib.phc_auto_reset_num_partials.argtypes, lib.phc_auto_reset_num_partials.restype = [], I
+    lib.phc_auto_reset_scratch_bytes.argtypes, lib.phc_auto_reset_scratch_bytes.restype = [I64], I64
+    lib.phc_auto_reset.argtypes = [C.POINTER(MotionTables), C.POINTER(ResetEnv), C.POINTER(ResetBook), C.POINTER(ResetCfg), P, I64, P, P, P,
+                                   P, P, P]
+    lib.phc_stats_reduce.argtypes = [P, I, I, I64, P, P, I, P, I, P]
     lib.phc_build_motion_tables.argtypes = [C.POINTER(BuildIn), C.POINTER(BuildOut), P]
     lib.phc_build_motion_aa.argtypes = [P, I, P, P, I64, I64, P, P, P, P, P]
     lib.phc_cast_f64_f32.argtypes = [P, I64, P, P]
@@ -119,7 +143,7 @@ def _declare(lib):
     lib.phc_frame_blend.argtypes = [P, P, P, P, I64, P, P, P, P]
     for name in EXPORTS:
         fn = getattr(lib, name)
-        if fn.restype is C.c_int and name not in ("phc_version", "phc_step_num_partials"):
+        if fn.restype is C.c_int and name not in ("phc_version", "phc_step_num_partials", "phc_auto_reset_num_partials"):
             fn.restype = I
 
 

@@ -55,11 +55,15 @@ class StepConfig:
 class FusedStep:
     def __init__(self, motion_lib: MotionLibBase, num_envs: int, cfg: Optional[StepConfig] = None,
                  rms: Optional[RunningNorm] = None, normalize: bool = False, accumulate_moments: bool = False,
-                 debug_ref: bool = False, defer_moments: bool = False):
+                 debug_ref: bool = False, defer_moments: bool = False, metrics: bool = False):
         """``accumulate_moments``: the kernel also produces the fp64 column sums ``RunningNorm.update`` needs.  By default they
         are folded into ``rms``' pending moments after every step (one tiny reduce launch).  ``defer_moments=True`` lets the
         kernel ADD every step's sums to its per-CTA slots instead; call ``flush_moments()`` once per rollout (before
-        ``rms.finalize()``) -- no per-step reduce launch at all."""
+        ``rms.finalize()``) -- no per-step reduce launch at all.
+
+        ``metrics``: the kernel also sums the episode metrics the reference logs (reference puffer_phc/clean_pufferl/env.py:102-110:
+        env-steps, reward, the five reward_raw columns, resets, terminations) into per-CTA fp64 slots; ``flush_moments()`` folds
+        them into ``self.stats[1 + 2 * 934:]`` (``metric_values()``), the tail of the ONE buffer ``rms.finalize()`` all-reduces."""
         self.lib = _ffi.load()
         self.motion_lib = motion_lib
         self.cfg = cfg or StepConfig()
@@ -69,7 +73,7 @@ class FusedStep:
         self.rms = rms
         self.normalize = bool(normalize)
         self.accumulate_moments = bool(accumulate_moments)
-        self.defer_moments = bool(defer_moments) and self.accumulate_moments
+        self.defer_moments = bool(defer_moments) and (self.accumulate_moments or bool(metrics))
         self._pending_rows = 0
         if (normalize or accumulate_moments) and rms is None:
             raise ValueError("normalize / accumulate_moments need a RunningNorm")
@@ -84,8 +88,17 @@ class FusedStep:
         self.terminate_buf = torch.ones(self.N, dtype=torch.bool, device=dev)
         self.termination_distances = torch.full((NUM_BODIES,), float(c.termination_distance), dtype=torch.float32, device=dev)
         self.num_partials = int(self.lib.phc_step_num_partials())
-        self.partials = (torch.zeros((self.num_partials, 2, OBS_DIM), dtype=torch.float64, device=dev)
+        # one slot per CTA of the step kernel, then one per CTA of the auto-reset tail (its moment corrections, envs/reset.py)
+        self.num_tail_partials = int(self.lib.phc_auto_reset_num_partials())
+        self.partials = (torch.zeros((self.num_partials + self.num_tail_partials, 2, OBS_DIM), dtype=torch.float64, device=dev)
                          if accumulate_moments else None)
+        self.metrics = bool(metrics)
+        self.metric_partials = torch.zeros((self.num_partials, _ffi.NUM_METRICS), dtype=torch.float64, device=dev) if metrics else None
+        self.row_adjust = torch.zeros(1, dtype=torch.float64, device=dev)
+        # the rank's statistics buffer: [n, sum x, sum x^2 | episode metrics] -- moments and metrics travel in one all-reduce
+        self.stats = torch.zeros(1 + 2 * OBS_DIM + _ffi.NUM_METRICS, dtype=torch.float64, device=dev)
+        if rms is not None and (accumulate_moments or metrics):
+            rms.attach_stats(self.stats)
         self.ref_t = torch.zeros((self.N, 312), dtype=torch.float32, device=dev) if debug_ref else None
         self.ref_t1 = torch.zeros((self.N, 312), dtype=torch.float32, device=dev) if debug_ref else None
         mask = 0
@@ -155,15 +168,16 @@ class FusedStep:
             raw.stride(0), reset.data_ptr(), term.data_ptr(), self.partials.data_ptr() if self.accumulate_moments else None,
             1 if self.defer_moments else 0,
             self.ref_t[row0:].data_ptr() if self.ref_t is not None else None,
-            self.ref_t1[row0:].data_ptr() if self.ref_t1 is not None else None)
+            self.ref_t1[row0:].data_ptr() if self.ref_t1 is not None else None,
+            self.metric_partials.data_ptr() if self.metrics else None)
         with torch.cuda.device(self.device):
             _ffi.check(self.lib.phc_step_fused(C.byref(self.motion_lib.ctables), C.byref(sin), C.byref(self._ccfg), C.byref(sout),
                                                _ffi.stream_ptr()), "phc_step_fused")
             if self.defer_moments:
                 if not torch.cuda.is_current_stream_capturing():      # a capture runs no kernel: replays are counted by count_replayed()
                     self._pending_rows += N
-            elif self.accumulate_moments:
-                self.rms.accumulate_partials(self.partials, N)
+            elif self.accumulate_moments or self.metrics:
+                self._reduce(N, zero=False)
         res = {"obs": obs, "reward": rew, "reward_raw": raw, "reset": reset, "terminated": term}
         if self.normalize:
             res["obs_norm"] = obs_norm
@@ -175,13 +189,30 @@ class FusedStep:
         if self.defer_moments:
             self._pending_rows += int(steps) * self.N
 
+    def _reduce(self, rows: int, zero: bool) -> None:
+        """phc_stats_reduce: per-CTA moment / metric partials (+ the auto-reset tail's corrections) -> ``self.stats``."""
+        mp = self.partials if self.accumulate_moments else None
+        _ffi.check(self.lib.phc_stats_reduce(_ffi.ptr(mp), 0 if mp is None else (mp.shape[0] if self.defer_moments else self.num_partials),
+                                             OBS_DIM, int(rows) if mp is not None else 0, _ffi.ptr(self.row_adjust) if mp is not None else None,
+                                             _ffi.ptr(self.metric_partials), self.num_partials if self.metrics else 0,
+                                             _ffi.ptr(self.stats), 1 if zero else 0, _ffi.stream_ptr()), "phc_stats_reduce")
+
     def flush_moments(self) -> None:
-        """``defer_moments`` mode: fold the sums the kernel has accumulated since the last flush into ``rms``' pending moments."""
+        """``defer_moments`` mode: fold the sums the kernel has accumulated since the last flush (moments, the auto-reset tail's
+        corrections and the episode metrics) into ``self.stats`` and clear the per-CTA slots -- ONE launch."""
         if self.defer_moments and self._pending_rows:
             with torch.cuda.device(self.device):
-                self.rms.accumulate_partials(self.partials, self._pending_rows)
-                self.partials.zero_()
+                self._reduce(self._pending_rows, zero=True)
             self._pending_rows = 0
+
+    def metric_values(self, reset: bool = False) -> Dict[str, float]:
+        """The accumulated episode metrics as a dict (one device->host read of 16 doubles); after ``rms.finalize()`` on several
+        ranks they are the global sums.  ``reset`` clears them."""
+        m = self.stats[1 + 2 * OBS_DIM:]
+        v = m.cpu().tolist()
+        if reset:
+            m.zero_()
+        return {k: v[i] for i, k in enumerate(_ffi.METRIC_NAMES)}
 
     # ---- host-buffer entry (end-to-end path): H2D of the per-env inputs, the kernel, D2H of reward / flags ------------
     _HOST_KEYS = ("body_state", "progress", "start_time", "start_offset", "motion_ids", "global_offset", "dof_force", "dof_vel")
@@ -251,6 +282,7 @@ class FusedStep:
         # the warm-up's contribution (per-CTA slots / pending moments) after it
         self.flush_moments()
         saved_moments = self.rms.moments_buffer().clone() if (self.accumulate_moments and self.rms is not None) else None
+        saved_metrics = self.stats[1 + 2 * OBS_DIM:].clone()
         side = torch.cuda.Stream(device=self.device)
         side.wait_stream(torch.cuda.current_stream(self.device))
         with torch.cuda.stream(side):
@@ -266,6 +298,9 @@ class FusedStep:
                 self._pending_rows = 0
             if saved_moments is not None:
                 self.rms.moments_buffer().copy_(saved_moments)
+        if self.metrics:
+            self.metric_partials.zero_()
+            self.stats[1 + 2 * OBS_DIM:].copy_(saved_metrics)
         graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(graph):
             res = self(*args, out=out)

@@ -24,6 +24,7 @@ class RunningNorm(nn.Module):
         self.epsilon = epsilon
         self.clip = clip
         self._moments = None      # fp64 [1 + 2C]: n, sum, sum of squares (device)
+        self._stats = None        # optional enclosing buffer [1 + 2C + NUM_METRICS] (attach_stats): what finalize() all-reduces
         self._scratch = None
 
     # ---- forward (running_norm.py:15-20) -----------------------------------------------------------
@@ -44,6 +45,14 @@ class RunningNorm(nn.Module):
         return y.view(x.shape)
 
     # ---- update (running_norm.py:23-34), split into accumulate / (all-reduce) / finalize -----------------
+    def attach_stats(self, stats: torch.Tensor) -> None:
+        """Make the pending moments the head of ``stats`` = fp64 ``[n, sum x (C), sum x^2 (C), episode metrics (NUM_METRICS)]`` -- the
+        rank's ONE statistics buffer (FusedStep.stats): ``finalize()`` then all-reduces moments and metrics as a single message."""
+        C_ = self.running_mean.shape[1]
+        assert stats.dtype == torch.float64 and stats.is_contiguous() and stats.numel() >= 1 + 2 * C_
+        self._stats = stats
+        self._moments = stats[: 1 + 2 * C_]
+
     def moments_buffer(self) -> torch.Tensor:
         C_ = self.running_mean.shape[1]
         if self._moments is None or self._moments.device != self.running_mean.device:
@@ -83,7 +92,8 @@ class RunningNorm(nn.Module):
         lib = _ffi.load()
         m = self.moments_buffer()
         if torch.distributed.is_available() and torch.distributed.is_initialized() and torch.distributed.get_world_size(group) > 1:
-            torch.distributed.all_reduce(m, op=torch.distributed.ReduceOp.SUM, group=group)
+            buf = self._stats if (self._stats is not None and self._moments.data_ptr() == self._stats.data_ptr()) else m
+            torch.distributed.all_reduce(buf, op=torch.distributed.ReduceOp.SUM, group=group)
         C_ = self.running_mean.shape[1]
         with torch.cuda.device(m.device):
             _ffi.check(lib.phc_rms_finalize(_ffi.ptr(m), C_, _ffi.ptr(self.running_mean), _ffi.ptr(self.running_var),
@@ -111,4 +121,5 @@ class RunningNorm(nn.Module):
         self.epsilon = state["epsilon"]
         self.clip = state["clip"]
         self._moments = None
+        self._stats = None
         self._scratch = None
