@@ -221,6 +221,45 @@ def run_reference(args, rank, world):
     print(json.dumps(line), flush=True)
 
 
+def multi_gpu_check(lib, T, N, rank, world, dev, n_check=8192):
+    """Every rank steps its own env shard once (seed 1000 + rank), the moments + episode metrics are all-reduced by
+    RunningNorm.finalize (one NCCL message), and then (a) all ranks must hold BIT-IDENTICAL running_mean / running_var / count /
+    metric sums and (b) rank 0 repeats the whole thing in one process over the concatenated shards: the result must agree within
+    1e-5 relative (the fp64 sums are associated differently)."""
+    import torch
+    import torch.distributed as dist
+    from puffer_phc_b200 import synth
+    from puffer_phc_b200.fused_step import FusedStep, StepConfig
+    from puffer_phc_b200.policies.running_norm import RunningNorm
+    keys = ("body_state", "progress", "start_time", "start_offset", "motion_ids", "global_offset", "dof_force", "dof_vel")
+
+    def run(shards, allreduce):
+        rms = RunningNorm(934).to(dev)
+        fs = FusedStep(lib, n_check, StepConfig(), rms=rms, normalize=True, accumulate_moments=True, defer_moments=True, metrics=True)
+        for r in shards:
+            S = synth.make_env_state(T, n_check, seed=1000 + r)
+            fs(*[S[k] for k in keys])
+        fs.flush_moments()
+        metrics_before = fs.stats[1 + 2 * 934:].clone()
+        rms.finalize(allreduce=allreduce)
+        return rms, (fs.stats[1 + 2 * 934:].clone() if allreduce else metrics_before)
+
+    rms, met = run([rank], True)
+    mine = torch.cat([rms.running_mean.reshape(-1).double(), rms.running_var.reshape(-1).double(), rms.count.double(), met])
+    allv = [torch.empty_like(mine) for _ in range(world)]
+    dist.all_gather(allv, mine)
+    identical = all(bool(torch.equal(allv[0].view(torch.int64), v.view(torch.int64))) for v in allv)
+    res = {"envs_per_rank": n_check, "ranks": world, "ranks_bit_identical": identical}
+    if rank == 0:
+        one, met1 = run(list(range(world)), False)
+        ref = torch.cat([one.running_mean.reshape(-1).double(), one.running_var.reshape(-1).double(), one.count.double(), met1])
+        err = (mine - ref).abs() / (1e-5 * ref.abs() + 1e-9)
+        res["vs_single_process_max_err_over_tol"] = float(err.max())
+        res["global_env_steps"] = float(met[0])
+        res["ok"] = bool(identical and float(err.max()) <= 1.0 and float(met[0]) == n_check * world)
+    return res
+
+
 def workload_config(envs, world, sample_note=None):
     cfg = {
         "workload": "config4/5: fused rollout-side step (2x motion-state + imitation obs/reward/reset + self obs + RMS norm "
@@ -283,7 +322,9 @@ def main():
     knob_norm, knob_mom = os.environ.get("PHC_BENCH_NORM", "1") != "0", os.environ.get("PHC_BENCH_MOM", "1") != "0"
     knob_gae_side = os.environ.get("PHC_BENCH_GAE_SIDE", "1") != "0"       # valid either way: where the GAE launch is queued
     # defer_moments: the kernel adds every step's column sums to its per-CTA slots; they are folded once per rollout (flush_moments)
-    fs = FusedStep(lib, N, StepConfig(), rms=rms, normalize=knob_norm, accumulate_moments=knob_mom, defer_moments=True)
+    # metrics: the kernel also sums the episode metrics (env-steps, reward, reward_raw[5], resets, terminations) per CTA; they ride in the
+    # same statistics buffer as the moments, so rms.finalize() all-reduces both in one message
+    fs = FusedStep(lib, N, StepConfig(), rms=rms, normalize=knob_norm, accumulate_moments=knob_mom, defer_moments=True, metrics=True)
     ins, outs = [], []
     for s in range(SETS):
         S = synth.make_env_state(T, N, seed=1 + rank + 100 * s)
@@ -317,9 +358,9 @@ def main():
             compute_gae_cuda(roll["dones"][lo:lo + N], roll["values"][lo:lo + N], roll["rewards"][lo:lo + N], 0.98, 0.2, out=adv[lo:lo + N])
         launches["n"] += 2
         if ((i + 1) % HORIZON == 0 or last) and knob_mom:
-            fs.flush_moments()                         # fold the per-CTA sums of the whole rollout (1 reduce + 1 memset)
-            rms.finalize()                             # all-reduce of the fp64 moments (N>1) + running-average update
-            launches["n"] += 2                         # phc_rms_reduce_partials + phc_rms_finalize (the two memsets are torch's)
+            fs.flush_moments()                         # phc_stats_reduce: folds + clears the per-CTA moment / metric sums of the rollout
+            rms.finalize()                             # ONE all-reduce of [moments | episode metrics] (N>1) + running-average update
+            launches["n"] += 2                         # phc_stats_reduce + phc_rms_finalize (the one memset is torch's)
         if last:
             stream.wait_stream(gae_stream)             # the timed region ends when both streams have drained
 
@@ -377,10 +418,63 @@ def main():
                "note": "H2D: PhysX record + per-env scalars + dof force/vel from pinned memory; D2H: reward, reward_raw, reset, "
                        "terminated (what the reference moves to the host each step, clean_pufferl/structs.py:123-128); obs stays in HBM for the policy"}
 
+    # ---- N > 1: numerical self-check of the one exchange step (outside every timed region) --------------------------------------
+    check = None
+    if world > 1:
+        check = multi_gpu_check(lib, T, N, rank, world, dev)
+
     # ---- the smaller BASELINE configs, reported beside the headline (rank 0, N=1 only; not the bench line) ---------------
     other = None
     if world == 1 and not args.no_other_configs:
         other = {}
+        # ---- the step FOLLOWED BY the device-side auto-reset (row f1): same 65536 envs, ~14 % of them flagged each step ---------------
+        from puffer_phc_b200.envs.reset import AutoReset, EnvTensors
+        keys_r = ("body_state", "progress", "start_time", "start_offset", "global_offset")
+        pristine = [{k: ins[s_][k].clone() for k in keys_r} for s_ in range(SETS)]
+        ars = []
+        for s_ in range(SETS):
+            S_, O_ = ins[s_], outs[s_]
+            env_ = EnvTensors(rigid_body_state=S_["body_state"], humanoid_root_states=torch.empty(N, 13, device=dev),
+                              dof_pos=torch.empty(N, 69, device=dev), dof_vel=S_["dof_vel"], progress_buf=S_["progress"],
+                              reset_buf=O_["reset"], terminate_buf=O_["terminated"], global_offset=S_["global_offset"],
+                              motion_start_times=S_["start_time"], motion_start_times_offset=S_["start_offset"],
+                              sampled_motion_ids=S_["motion_ids"], obs_buf=O_["obs"])
+            ars.append(AutoReset(env_, lib, obs_norm=O_["obs_norm"], rms=rms, fused=fs))
+        phase_r = torch.rand(N, device=dev)
+        Kr = 200
+        ra = [torch.cuda.Event(enable_timing=True) for _ in range(Kr)]
+        rm = [torch.cuda.Event(enable_timing=True) for _ in range(Kr)]
+        rb = [torch.cuda.Event(enable_timing=True) for _ in range(Kr)]
+        n_flagged = 0
+        for i in range(-8, Kr):
+            s_ = i % SETS
+            S_, O_ = ins[s_], outs[s_]
+            if i >= 0:
+                ra[i].record(stream)
+            fs(S_["body_state"], S_["progress"], S_["start_time"], S_["start_offset"], S_["motion_ids"], S_["global_offset"], S_["dof_force"], S_["dof_vel"], out=O_)
+            if i >= 0:
+                rm[i].record(stream)
+            ars[s_](O_["reward"], O_["reward_raw"], phase_r)
+            if i >= 0:
+                rb[i].record(stream)
+            for k in keys_r:                         # untimed: put the set back so that every pass resets the same ~14 % of the envs
+                S_[k].copy_(pristine[s_][k])
+            if i == Kr - 1:
+                n_flagged = int(ars[s_].reset_count)
+        torch.cuda.synchronize()
+        fs.flush_moments()
+        fs.stats.zero_()
+        us_step = sum(a_.elapsed_time(b_) for a_, b_ in zip(ra, rm)) / Kr * 1e3
+        us_tail = sum(a_.elapsed_time(b_) for a_, b_ in zip(rm, rb)) / Kr * 1e3
+        # algorithmic bytes of the tail per FLAGGED env: 2 queries x 2 frames x 1248 + lrs/dvs 2 x (384 + 276) + meta 48 read; state 1248
+        # + root 52 + dof 552 + obs old 3736 read / new 3736 + norm 3736 written; + 7 B/env of flags, rewards and bookkeeping for every env
+        tail_bytes = n_flagged * (4 * 1248 + 2 * 660 + 48 + 1248 + 52 + 552 + 3 * 3736) + N * 27
+        other["step_plus_reset_65536_envs"] = {
+            "us_step": us_step, "us_auto_reset": us_tail, "us_total": us_step + us_tail, "flagged_envs_per_step": n_flagged,
+            "env_steps_per_s": N / ((us_step + us_tail) * 1e-6), "auto_reset_gbs": tail_bytes / (us_tail * 1e-6) / 1e9,
+            "note": "phc_step_fused then phc_auto_reset (2 launches: ordered compaction + bookkeeping over all envs, then state write + "
+                    "subset observation + moment correction for the flagged ones), no host synchronisation; CUDA-event timed per pass, "
+                    "inputs restored between passes (untimed) so every pass resets the same share of the envs"}
         n2 = 4096                                                            # config 2: 4096 envs, fused obs/reward/reset kernel
         rms2 = RunningNorm(934).to(dev)
         fs2 = FusedStep(lib, n2, StepConfig(), rms=rms2, normalize=True, accumulate_moments=True, defer_moments=True)
@@ -442,6 +536,10 @@ def main():
         }
         if not (knob_norm and knob_mom):
             line["invalid"] = "tuning run: PHC_BENCH_NORM/PHC_BENCH_MOM dropped work from the step"
+        if check:
+            line["multi_gpu_check"] = check
+            print(f"[bench] N>1 check: ranks bit-identical = {check['ranks_bit_identical']}, vs single-process run over all envs "
+                  f"max err/tol = {check['vs_single_process_max_err_over_tol']:.3f} -> {'OK' if check['ok'] else 'FAILED'}", file=sys.stderr)
         if e2e:
             line["e2e"] = e2e
         if other:

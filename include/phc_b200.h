@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define PHC_B200_VERSION 110 /* 0.1.1 */
+#define PHC_B200_VERSION 120 /* 0.1.2 */
 
 enum {
     PHC_OK = 0,
@@ -85,6 +85,13 @@ typedef struct phc_motion_tables {
     const float *limb_weights;   /* [M,10] _motion_limb_weights                      */
     const float *packed;         /* optional [F,312]: per frame gts|grs|gvs|gavs rows back to back, written by
                                     phc_pack_frames(); NULL = gather from the four separate tables */
+    const float *pair_aux;       /* optional [F,24,2], 16-byte aligned, written by phc_build_pair_aux(): what slerp needs to know
+                                    about the rotation pair (grs[f], grs[min(f+1, last frame of the clip)]) of every body --
+                                    h = acos|q0.q1| and +-1/sqrt(1-(q0.q1)^2), or the fall-back codes -- computed once per pair with
+                                    the very operations the kernels use at query time (bit-identical results)          */
+    const uint8_t *pair_flags;   /* optional [F]: bit 0 = some body of the pair takes slerp's un-normalised midpoint fall-back
+                                    (|sin_half| < 0.001), i.e. frame f+1 is needed even when blend == 0                */
+    int pair_device;             /* PHC_REF_DEVICE_* the pair tables were built for (the dot product's summation order) */
     int64_t F, M;
 } phc_motion_tables;
 
@@ -92,6 +99,12 @@ typedef struct phc_motion_tables {
  * (B200 layout: one contiguous 1248 B gather per frame instead of four 288/384 B ones).
  * packed: caller-allocated [F,312] fp32, 16-byte aligned. */
 int phc_pack_frames(const phc_motion_tables *t, float *packed, phc_stream_t stream);
+
+/* Pair tables of the fused step (see phc_motion_tables.pair_aux): with them a query whose time sits exactly on a table frame
+ * (blend == 0: ~84 % of the queries when control and motion run at the same rate) gathers ONE frame record + 192 B instead of two
+ * records, and no query evaluates acos / sqrt / reciprocal of the pair again.  Needs grs, num_frames, length_starts. */
+int phc_build_pair_aux(const phc_motion_tables *t, int ref_device, float *pair_aux /* [F,24,2] */, uint8_t *pair_flags /* [F] */,
+                       phc_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------- */
 /* Motion TABLE BUILD ("next" row f4): MotionLibSMPL.load_motion_with_skeleton                   */

@@ -17,14 +17,14 @@ _lib = None
 c_f32p, c_i64p, c_u8p, c_i16p, c_f64p = C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p
 
 EXPORTS = (
-    "phc_version", "phc_last_error", "phc_pack_frames", "phc_motion_state", "phc_reset_ref_state", "phc_sample_time_interval",
+    "phc_version", "phc_last_error", "phc_pack_frames", "phc_build_pair_aux", "phc_motion_state", "phc_reset_ref_state", "phc_sample_time_interval",
     "phc_imitation_obs_v6", "phc_self_obs_smpl_max", "phc_amp_obs_smpl", "phc_imitation_reward", "phc_im_reset",
     "phc_step_num_partials", "phc_step_fused", "phc_rms_forward", "phc_rms_scratch_doubles", "phc_rms_moments",
     "phc_rms_reduce_partials", "phc_rms_finalize", "phc_auto_reset_num_partials", "phc_auto_reset_scratch_bytes", "phc_auto_reset",
     "phc_stats_reduce", "phc_gae", "phc_build_motion_tables", "phc_build_motion_aa", "phc_cast_f64_f32", "phc_mpjpe", "phc_frame_blend",
 )
 
-VERSION = 110
+VERSION = 120
 NUM_METRICS = 16
 METRIC_NAMES = ("steps", "reward", "r_pos", "r_rot", "r_vel", "r_ang_vel", "r_power", "resets", "terminations", "truncations",
                 "episode_return", "episode_length", "episodes")
@@ -42,7 +42,8 @@ TABLE_FIELDS = ("gts", "grs", "lrs", "gvs", "gavs", "dvs", "motion_aa", "motion_
 
 
 class MotionTables(C.Structure):
-    _fields_ = [(k, C.c_void_p) for k in TABLE_FIELDS] + [("F", C.c_int64), ("M", C.c_int64)]
+    _fields_ = [(k, C.c_void_p) for k in TABLE_FIELDS] + [("pair_aux", C.c_void_p), ("pair_flags", C.c_void_p), ("pair_device", C.c_int),
+                                                          ("F", C.c_int64), ("M", C.c_int64)]
 
 
 STATE_FIELDS = ("root_pos", "root_rot", "dof_pos", "root_vel", "root_ang_vel", "dof_vel", "motion_aa", "rg_pos", "rb_rot",
@@ -115,6 +116,7 @@ def _declare(lib):
     lib.phc_version.argtypes, lib.phc_version.restype = [], I
     lib.phc_last_error.argtypes, lib.phc_last_error.restype = [], C.c_char_p
     lib.phc_pack_frames.argtypes = [C.POINTER(MotionTables), P, P]
+    lib.phc_build_pair_aux.argtypes = [C.POINTER(MotionTables), I, P, P, P]
     lib.phc_motion_state.argtypes = [C.POINTER(MotionTables), P, P, P, I64, C.POINTER(MotionStateOut), I, P]
     lib.phc_reset_ref_state.argtypes = [C.POINTER(MotionTables), P, P, P, P, I64, P, P, P, P, I64, I, P]
     lib.phc_sample_time_interval.argtypes = [P, P, I64, I, P, P]
@@ -188,7 +190,12 @@ def load() -> C.CDLL:
     with _lock:
         if _lib is None:
             path = _build.LIB_PATH
-            if not os.path.isfile(path) or _build.needs_build():
+            alt = os.environ.get("PHC_B200_LIB")          # tuning builds (profiles/tools/ab_variants.py): an explicit, prebuilt library
+            if alt:
+                if not os.path.isfile(alt):
+                    raise RuntimeError(f"PHC_B200_LIB={alt} does not exist")
+                path = alt
+            elif not os.path.isfile(path) or _build.needs_build():
                 try:
                     _build.build()
                 except Exception as exc:  # no nvcc and no prebuilt library

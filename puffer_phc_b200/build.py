@@ -43,12 +43,14 @@ def needs_build() -> bool:
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
-    if not force and not needs_build():
+def build(force: bool = False, verbose: bool = False, out: str = None, extra_flags=()) -> str:
+    """``out`` / ``extra_flags``: tuning builds into another path (e.g. -DST_WHINT=200), selected at run time with PHC_B200_LIB."""
+    target = out or LIB_PATH
+    if out is None and not force and not needs_build():
         return LIB_PATH
-    os.makedirs(LIB_DIR, exist_ok=True)
-    extra = os.environ.get("PHC_NVCC_EXTRA", "").split()      # e.g. -DST_MIN_CTAS=2 for tuning experiments
-    cmd = [_nvcc(), *NVCC_FLAGS, *extra, "-o", LIB_PATH, *sources()]
+    os.makedirs(os.path.dirname(target), exist_ok=True)
+    extra = os.environ.get("PHC_NVCC_EXTRA", "").split() + list(extra_flags)      # e.g. -DST_MIN_CTAS=2 for tuning experiments
+    cmd = [_nvcc(), *NVCC_FLAGS, *extra, "-o", target, *sources()]
     if verbose:
         cmd += ["-Xptxas", "-v"]
         print(" ".join(cmd))
@@ -57,7 +59,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
         sys.stderr.write(res.stdout + res.stderr)
     if res.returncode != 0:
         raise RuntimeError("nvcc failed building libphc_b200.so")
-    return LIB_PATH
+    return target
 
 
 if __name__ == "__main__":

@@ -173,9 +173,43 @@ __global__ void pack_frames_kernel(const phc_motion_tables T, float* __restrict_
     }
 }
 
+// pair_aux[f][j] = slerp_pair_make(grs[f][j], grs[f1][j]) with f1 = min(f + 1, last frame of f's clip); pair_flags[f] bit 0 = some
+// body takes the midpoint fall-back.  One warp per frame, lane = body; the clip of a frame by binary search over length_starts.
+__global__ void __launch_bounds__(128) pair_aux_kernel(const phc_motion_tables T, int dev, float* __restrict__ aux, uint8_t* __restrict__ flags) {
+    const int lane = threadIdx.x & 31;
+    const int64_t f = (int64_t)blockIdx.x * 4 + (threadIdx.x >> 5);
+    if (f >= T.F) return;
+    int64_t lo = 0, hi = T.M;                     // largest clip with length_starts <= f
+    while (hi - lo > 1) {
+        const int64_t mid = (lo + hi) >> 1;
+        if (__ldg(T.length_starts + mid) <= f) lo = mid; else hi = mid;
+    }
+    const int64_t last = __ldg(T.length_starts + lo) + __ldg(T.num_frames + lo) - 1;
+    const int64_t f1 = f + 1 <= last ? f + 1 : last;
+    bool mid2 = false;
+    if (lane < NB) {
+        const SlerpPair sp = slerp_pair_make(ldg4a(T.grs + (f * NB + lane) * 4), ldg4a(T.grs + (f1 * NB + lane) * 4), dev);
+        *reinterpret_cast<float2*>(aux + (f * NB + lane) * 2) = make_float2(sp.h, sp.inv);
+        mid2 = sp.h == -2.0f;
+    }
+    const bool any = __any_sync(FULL, mid2);
+    if (lane == 0) flags[f] = any ? 1 : 0;
+}
+
 }  // namespace phc
 
 using namespace phc;
+
+extern "C" int phc_build_pair_aux(const phc_motion_tables* t, int ref_device, float* pair_aux, uint8_t* pair_flags, phc_stream_t stream) {
+    const char* fn = "phc_build_pair_aux";
+    PHC_REQUIRE(t && pair_aux && pair_flags, PHC_EINVAL, "%s: NULL pointer", fn);
+    PHC_REQUIRE(t->grs && t->num_frames && t->length_starts, PHC_EINVAL, "%s: grs / num_frames / length_starts required", fn);
+    PHC_REQUIRE(aligned16(t->grs) && aligned8(pair_aux), PHC_EALIGN, "%s: grs must be 16-byte, pair_aux 8-byte aligned", fn);
+    PHC_REQUIRE(ref_device == PHC_REF_DEVICE_CPU || ref_device == PHC_REF_DEVICE_CUDA, PHC_EINVAL, "%s: ref_device must be 0 or 1", fn);
+    if (t->F <= 0 || t->M <= 0) return PHC_OK;
+    pair_aux_kernel<<<(unsigned)((t->F + 3) / 4), 128, 0, (cudaStream_t)stream>>>(*t, ref_device, pair_aux, pair_flags);
+    return check_launch(fn);
+}
 
 extern "C" int phc_motion_state(const phc_motion_tables* t, const int64_t* motion_ids, const float* motion_times,
                                 const float* offset, int64_t B, const phc_motion_state_out* out, int ref_device, phc_stream_t stream) {

@@ -25,6 +25,28 @@ PHC_HD BodyState blend_frames(const BodyState& a, const BodyState& b, float blen
 }
 
 
+// The same blend with the pair's slerp quantities read from the motion library's pair-aux table (bit-identical to blend_frames).
+PHC_HD BodyState blend_frames_pair(const BodyState& a, const BodyState& b, float blend, V3 off, SlerpPair sp) {
+    const float om = 1.0f - blend;
+    BodyState r;
+    r.p = V3{lerp(a.p.x, b.p.x, om, blend) + off.x, lerp(a.p.y, b.p.y, om, blend) + off.y, lerp(a.p.z, b.p.z, om, blend) + off.z};
+    r.q = slerp_pair(a.q, b.q, blend, sp);
+    r.v = V3{fmaf(blend, b.v.x, om * a.v.x), fmaf(blend, b.v.y, om * a.v.y), fmaf(blend, b.v.z, om * a.v.z)};
+    r.w = V3{fmaf(blend, b.w.x, om * a.w.x), fmaf(blend, b.w.y, om * a.w.y), fmaf(blend, b.w.z, om * a.w.z)};
+    return r;
+}
+// blend == 0 exactly (the query time sits on a table frame: ~84 % of the queries when control and motion run at the same rate) and no
+// body of the pair takes the midpoint fall-back: frame 1 only ever contributes 0 * x = +-0, so it is neither fetched nor read.
+// Equal to blend_frames(a, b, 0, off) up to the sign of an exact zero.
+PHC_HD BodyState blend_frames_t0(const BodyState& a, V3 off, SlerpPair sp) {
+    BodyState r;
+    r.p = V3{a.p.x + off.x, a.p.y + off.y, a.p.z + off.z};
+    r.q = slerp_pair_t0(a.q, sp);
+    r.v = a.v;
+    r.w = a.w;
+    return r;
+}
+
 // compute_imitation_observations_v6 for one body (common.py:137-173); b = simulated body, r = reference body.
 PHC_HD void task_obs_body(const BodyState& b, const BodyState& r, V3 root_pos, float hz, float hw, float* o_dpos,
                           float* o_drot, float* o_dvel, float* o_dang, float* o_lpos, float* o_lrot) {

@@ -299,6 +299,41 @@ PHC_HD Q4 slerp_rcp(Q4 q0, Q4 q1, float t, int dev = PHC_REF_CPU) {
     return Q4{ra * q0.x + rb * q1.x, ra * q0.y + rb * q1.y, ra * q0.z + rb * q1.z, ra * q0.w + rb * q1.w};
 }
 
+// ---- slerp with the pair quantities precomputed (motion library "pair aux" table, csrc/motion_state.cu) ---------------------------
+// Everything in slerp that depends only on the two table rotations -- the dot product c, the sign flip, the two fall-back decisions,
+// h = acos(c) and 1/sqrt(1-c*c) -- is a property of the frame pair (f, f+1), not of the query.  slerp_pair_make() computes it ONCE per
+// pair with exactly the operations slerp_rcp() uses (so the results are bit-identical), the fused step reads it back as two floats:
+//     h >= 0 : regular slerp, inv = +-1/sin_half (sign = the reference's q1 = -q1 flip)
+//     h = -1 : |cos| >= 1             -> q0
+//     h = -2 : |sin_half| < 0.001     -> 0.5*q0 + 0.5*(+-q1), inv = +-1
+struct SlerpPair { float h, inv; };
+PHC_HD SlerpPair slerp_pair_make(Q4 q0, Q4 q1, int dev) {
+    float c = dot4(q0, q1, dev);
+    const float sgn = c < 0.0f ? -1.0f : 1.0f;
+    c = fabsf(c);
+    if (c >= 1.0f) return SlerpPair{-1.0f, 1.0f};
+    const float s = sqrtf(1.0f - c * c);
+    if (fabsf(s) < 0.001f) return SlerpPair{-2.0f, sgn};
+    return SlerpPair{acosf(c), sgn * (1.0f / s)};
+}
+PHC_HD Q4 slerp_pair(Q4 q0, Q4 q1, float t, SlerpPair a) {
+    if (a.h == -1.0f) return q0;
+    if (a.h == -2.0f) {
+        const float hb = 0.5f * a.inv;
+        return Q4{0.5f * q0.x + hb * q1.x, 0.5f * q0.y + hb * q1.y, 0.5f * q0.z + hb * q1.z, 0.5f * q0.w + hb * q1.w};
+    }
+    const float ia = fabsf(a.inv);
+    const float ra = sin_0_halfpi((1.0f - t) * a.h) * ia;
+    const float rb = sin_0_halfpi(t * a.h) * a.inv;
+    return Q4{ra * q0.x + rb * q1.x, ra * q0.y + rb * q1.y, ra * q0.z + rb * q1.z, ra * q0.w + rb * q1.w};
+}
+// t == 0 and not the midpoint fall-back (h == -2, the caller's business): the second rotation contributes rb * q1 = +-0 only
+PHC_HD Q4 slerp_pair_t0(Q4 q0, SlerpPair a) {
+    if (a.h < 0.0f) return q0;
+    const float ra = sin_0_halfpi(a.h) * fabsf(a.inv);
+    return Q4{ra * q0.x, ra * q0.y, ra * q0.z, ra * q0.w};
+}
+
 // exp_map_to_quat (torch_utils.py:333-365) = quat_from_angle_axis(exp_map_to_angle_axis(e)); norms use the CPU reference's
 // fma chain, the small-angle mask falls back to angle 0 about (0,0,1).
 PHC_HD Q4 exp_map_to_quat(V3 e, int dev = PHC_REF_CPU) {

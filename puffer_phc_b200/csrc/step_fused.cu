@@ -84,9 +84,35 @@ constexpr int ST_WTHREADS = ST_WWARPS * 32;
 constexpr int ST_THREADS = (ST_CWARPS + ST_WWARPS + 1) * 32;     // + the planner warp
 constexpr int ST_PLANS = 4;                          // plan ring: plans are produced three iterations ahead (a ring of 8 with its own
                                                      // "free" barriers, seven ahead, measured slower: 0.186 vs 0.176 ms)
+// Ring of per-iteration metric records handed from role A's leader lanes to the writers.  Role A is never more than 5 iterations
+// ahead of the writers (its plan it+1 needs full[it-2], role B's tile it-2 needed empty[] of tile it-4), so a ring of 8 needs no wait.
+constexpr int ST_META = 8;
 constexpr int ST_WPAIRS = (OBS_W / 2 + ST_WTHREADS - 1) / ST_WTHREADS;  // column pairs owned by a writer thread
 constexpr int ST_DOF_F = 144;                        // dof_force (69, padded to 72) | dof_vel (69, padded to 72)
-constexpr int ST_WBUF_F = 3 * FRAME_F + ST_DOF_F;    // per compute warp: sim record | frame 0 | frame 1 | dof force/vel
+constexpr int ST_AUX_F = 2 * NB;                     // slerp pair quantities of frame 0's pair: (h, +-1/sin_half) per body
+constexpr int ST_AUX_OFF = 3 * FRAME_F + ST_DOF_F;
+constexpr int ST_WBUF_F = ST_AUX_OFF + ST_AUX_F;     // per (env, role): sim record | frame 0 | frame 1 | dof force/vel | pair aux
+// diagnosis builds (profiles/tools/ab_variants.py): compile single round-2 additions out to price them
+#ifndef ST_DIAG_NOMETRICS
+#define ST_DIAG_NOMETRICS 0
+#endif
+#ifndef ST_DIAG_NOEVAL
+#define ST_DIAG_NOEVAL 0
+#endif
+#ifndef ST_DIAG_DEV0
+#define ST_DIAG_DEV0 0
+#endif
+#ifndef ST_DIAG_NOFULLWAIT
+#define ST_DIAG_NOFULLWAIT 0
+#endif
+#if ST_DIAG_DEV0
+#define ST_DEV(cfg) 0
+#else
+#define ST_DEV(cfg) (cfg).ref_device
+#endif
+#ifndef ST_USE_AUX
+#define ST_USE_AUX 1                                 // 0: ignore the motion library's pair tables (A/B builds)
+#endif
 constexpr unsigned SPIN_LIMIT = 1u << 22;            // a stuck mbarrier traps (after a few seconds) instead of hanging the GPU
 
 // -DST_PROFILE=1: lane 0 of every compute warp accumulates the clock cycles it spends in each wait of its loop
@@ -115,6 +141,7 @@ struct StepArgs {
     int sim_vec;          // body_state rows are 16-byte aligned -> 16-byte cp.async staging
     int obs_vec;          // obs tiles are contiguous and 16-byte aligned -> TMA bulk tile stores
     int64_t num_blocks;   // ceil(N / S)
+    int use_aux;          // the motion library's pair tables exist and were built for cfg.ref_device
 };
 
 // ---- async-copy / barrier primitives ------------------------------------------------------------------------
@@ -187,7 +214,7 @@ struct EnvPlan {
     float blend, t, mlen;
     float offx, offy, offz;
     int prog;
-    int valid;
+    int valid;           // bit 0: env < N; bit 1: blend == 0 fast path (frame 1 is neither fetched nor read)
 };
 
 // Planner lane: per-env scalars, motion meta and the role's frame-blend (reference op order, bit-exact).
@@ -214,7 +241,22 @@ __device__ __forceinline__ EnvPlan make_plan(const StepArgs& a, int64_t e, int r
     frame_blend(p.t, p.mlen, nf, mdt, i0, i1, p.blend);
     p.f0 = i0 + ls;
     p.f1 = i1 + ls;
+    // the query sits exactly on a table frame: frame 1 would only contribute 0 * x, so it is not fetched (pair tables of the motion
+    // library).  The one exception, a body whose pair takes slerp's un-normalised midpoint fall-back, is rare (frozen poses) and
+    // fetches its second rotation on demand in the compute warp -- deciding it here would cost the planner a third dependent load.
+    if (a.use_aux && p.f1 != p.f0 && p.blend == 0.0f) p.valid |= 2;
     return p;
+}
+
+// Eval variant of the termination test (common.py:342-346): mean of the per-body distances of the body subset, in torch's own
+// summation order for the chosen device.  Kept out of line: it runs once per env in eval mode only, and its local arrays and loops
+// must not sit in the instruction stream the three warp roles share.
+__device__ __noinline__ float eval_mean_distance(const float* dist8 /* stride 8 floats per body */, unsigned mask, int dev) {
+    float dsub[NB];
+    int n = 0;
+    for (int b2 = 0; b2 < NB; ++b2)
+        if ((mask >> b2) & 1u) dsub[n++] = dist8[b2 * 8];
+    return mean_ordered(dsub, n, dev);
 }
 
 // Stage one reference frame (pos 72 | rot 96 | vel 72 | ang 72 floats) into shared memory: 78 x 16-byte chunks,
@@ -244,7 +286,8 @@ template <bool PACKED>
 __device__ __forceinline__ void issue_env(const StepArgs& a, const EnvPlan& p, int64_t e, int role, float* wbuf, int j, uint64_t* lbar) {
     const phc_step_in& in = a.in;
     const float* rec = in.body_state + e * in.env_stride;
-    const bool two = p.f1 != p.f0;
+    const bool two = p.f1 != p.f0 && !(p.valid & 2);
+    if (a.use_aux && j < ST_AUX_F / 4) cp_async16(wbuf + ST_AUX_OFF + 4 * j, a.t.pair_aux + p.f0 * ST_AUX_F + 4 * j);
     if (PACKED && ST_TMA_LOADS) {
         if (j == 0) {
             const unsigned fbytes = FRAME_F * 4;
@@ -296,15 +339,16 @@ __device__ __forceinline__ void store_ref(float* dst, int j, const BodyState& r)
 
 // DEBUG_REF instantiates the optional ref_state_t / ref_state_t1 outputs (otherwise their predicated-off stores would still
 // take load/store issue slots in every lane).
-template <bool PACKED, bool DEBUG_REF>
+template <bool PACKED, bool DEBUG_REF, bool AUX>
 __global__ void __maxnreg__(ST_MAXREG) step_fused_kernel(const StepArgs a) {   // one persistent CTA per SM
+    static_assert(!AUX || (PACKED && !ST_TMA_LOADS), "the pair tables ride with the packed records and cp.async staging");
     extern __shared__ float4 smem4[];
     float* tiles = reinterpret_cast<float*>(smem4);                          // [ST_TILES][S][934]
     float* wbufs = tiles + ST_TILES * ST_ENVS * OBS_W;                       // [2][S][record | frame 0 | frame 1 | dof]
     float* red = wbufs + ST_NBUF * ST_WBUF_F;                                // [S][24][8]  per-body partials (role A)
     float* red2 = red + ST_ENVS * NB * 8;                                    // [S][6][4]   second-stage partial sums
-    float* macc = red2 + ST_ENVS * 24;                                       // [S][12]     per-slot metric sums of this launch (role A leaders)
-    EnvPlan* plans = reinterpret_cast<EnvPlan*>(macc + ST_ENVS * 12);        // [ST_PLANS][2S]
+    float* meta = red2 + ST_ENVS * 24;                                       // [ST_META][S][12] per-env metric values, role A -> writers
+    EnvPlan* plans = reinterpret_cast<EnvPlan*>(meta + ST_META * ST_ENVS * 12);   // [ST_PLANS][2S]
     uint64_t* bars = reinterpret_cast<uint64_t*>(plans + ST_PLANS * ST_NBUF);
     uint64_t* full = bars;                    // [ST_TILES] tile b written by all compute warps
     uint64_t* empty = bars + ST_TILES;        // [ST_TILES] tile b drained by the writers
@@ -337,13 +381,9 @@ __global__ void __maxnreg__(ST_MAXREG) step_fused_kernel(const StepArgs a) {   /
         if ((int64_t)blockIdx.x < a.num_blocks) {
             mbar_wait<ST_CHINT>(&pfull[0], 0);
             cur = plans[buf];
-            if (cur.valid) issue_env<PACKED>(a, cur, (int64_t)blockIdx.x * ST_ENVS + slot, role, wbuf, j, &lfull[buf]);
+            if (cur.valid & 1) issue_env<PACKED>(a, cur, (int64_t)blockIdx.x * ST_ENVS + slot, role, wbuf, j, &lfull[buf]);
         }
         cp_async_commit();
-        if (role == 0 && j == 0) {         // the leader lane of a slot owns that slot's metric sums for the whole launch
-#pragma unroll
-            for (int k = 0; k < 12; ++k) macc[slot * 12 + k] = 0.0f;
-        }
         int it = 0;
         PROF_DECL
         for (int64_t blk = blockIdx.x; blk < a.num_blocks; blk += gridDim.x, ++it) {
@@ -355,7 +395,7 @@ __global__ void __maxnreg__(ST_MAXREG) step_fused_kernel(const StepArgs a) {   /
             // ---- operands of this body: shared memory -> registers, blend the two frames ----------------
             PROF_BEGIN
             cp_async_wait_all();
-            if (PACKED && ST_TMA_LOADS && cur.valid) mbar_wait<ST_CHINT>(&lfull[buf], it & 1);   // the bulk loads of this env have landed
+            if (PACKED && ST_TMA_LOADS && (cur.valid & 1)) mbar_wait<ST_CHINT>(&lfull[buf], it & 1);   // the bulk loads of this env have landed
             group_sync(bar_id);                                                // the cp.async copies of all 96 lanes have landed
             PROF_END(0)
             BodyState body{}, ref{};
@@ -368,8 +408,24 @@ __global__ void __maxnreg__(ST_MAXREG) step_fused_kernel(const StepArgs a) {   /
                 const float* sj = wbuf + REC * j;
                 body = BodyState{ld3(sj), ld4(sj + 3), ld3(sj + 7), ld3(sj + 10)};
                 const BodyState F0 = read_frame(wbuf + FRAME_F, j);
-                const BodyState F1 = (cur.f1 == cur.f0) ? F0 : read_frame(wbuf + 2 * FRAME_F, j);
-                ref = blend_frames(F0, F1, cur.blend, V3{cur.offx, cur.offy, cur.offz}, cfg.ref_device);
+                const V3 off{cur.offx, cur.offy, cur.offz};
+                if (AUX) {
+                    const float2 ax = *reinterpret_cast<const float2*>(wbuf + ST_AUX_OFF + 2 * j);
+                    const SlerpPair sp{ax.x, ax.y};
+                    if (cur.valid & 2) {
+                        ref = blend_frames_t0(F0, off, sp);
+                        if (sp.h == -2.0f) {       // midpoint fall-back 0.5 q0 + 0.5 (+-q1): the only case that needs frame 1's rotation
+                            const float4 q1 = __ldg(reinterpret_cast<const float4*>(a.t.packed + cur.f1 * FRAME_F + 72 + 4 * j));
+                            ref.q = slerp_pair(F0.q, Q4{q1.x, q1.y, q1.z, q1.w}, 0.0f, sp);
+                        }
+                    } else {
+                        const BodyState F1 = (cur.f1 == cur.f0) ? F0 : read_frame(wbuf + 2 * FRAME_F, j);
+                        ref = blend_frames_pair(F0, F1, cur.blend, off, sp);
+                    }
+                } else {
+                    const BodyState F1 = (cur.f1 == cur.f0) ? F0 : read_frame(wbuf + 2 * FRAME_F, j);
+                    ref = blend_frames(F0, F1, cur.blend, off, ST_DEV(cfg));
+                }
                 if (role == 0 && in.dof_force && j < 23) {                         // humanoid_phc.py:1295-1303
                     const float* df = wbuf + 3 * FRAME_F + 3 * j;
                     power = (fabsf(df[0] * df[72]) + fabsf(df[1] * df[73])) + fabsf(df[2] * df[74]);
@@ -388,7 +444,7 @@ __global__ void __maxnreg__(ST_MAXREG) step_fused_kernel(const StepArgs a) {   /
                     mbar_wait<ST_CHINT>(&pfull[d], ((it + 1) / ST_PLANS) & 1);
                     PROF_END(1)
                     nxt = plans[d * ST_NBUF + buf];
-                    if (nxt.valid) issue_env<PACKED>(a, nxt, nblk * ST_ENVS + slot, role, wbuf, j, &lfull[buf]);
+                    if (nxt.valid & 1) issue_env<PACKED>(a, nxt, nblk * ST_ENVS + slot, role, wbuf, j, &lfull[buf]);
                 }
                 cp_async_commit();
             }
@@ -399,7 +455,7 @@ __global__ void __maxnreg__(ST_MAXREG) step_fused_kernel(const StepArgs a) {   /
             // is still writing that older tile (the plan wait below holds role A back everywhere except in a CTA's last
             // iteration, which has no next plan).  The wait is one try_wait that succeeds at once whenever role A is the slower role.
             if ((ST_A_WAITS_TILE || role == 1) && use >= 1) mbar_wait<ST_CHINT>(&empty[b], (use - 1) & 1);
-            else if (use >= 1) mbar_wait<ST_CHINT>(&full[b], (use - 1) & 1);
+            else if (!ST_DIAG_NOFULLWAIT && use >= 1) mbar_wait<ST_CHINT>(&full[b], (use - 1) & 1);
             PROF_END(2)
 
 #if ST_STRESS_DELAY == 1 || ST_STRESS_DELAY == 2
@@ -412,7 +468,7 @@ __global__ void __maxnreg__(ST_MAXREG) step_fused_kernel(const StepArgs a) {   /
                     float sp, sr, sv, sa, dist = 0.0f;
                     reward_terms_body_fma(body, ref, sp, sr, sv, sa);
                     if ((cfg.reset_body_mask >> j) & 1u) {
-                        dist = norm3(body.p - ref.p, cfg.ref_device);
+                        dist = norm3(body.p - ref.p, ST_DEV(cfg));
                         if (!cfg.use_mean) dist = (dist > __ldg(in.term_dist + j)) ? 1.0f : 0.0f;     // common.py:347-350 (any)
                     }
                     *reinterpret_cast<float4*>(rj) = make_float4(sp, sr, sv, sa);
@@ -455,12 +511,11 @@ __global__ void __maxnreg__(ST_MAXREG) step_fused_kernel(const StepArgs a) {   /
                     if (cfg.enable_early_termination) {
                         if (cfg.use_mean) {                                               // common.py:342-346
                             const int first = __ffs(cfg.reset_body_mask) - 1;
-                            // torch's own summation order over the body subset (eval mode only; the per-body distances are still in smem)
-                            float dsub[NB];
-                            int n = 0;
-                            for (int b2 = 0; b2 < NB; ++b2)
-                                if ((cfg.reset_body_mask >> b2) & 1u) dsub[n++] = red[(slot * NB + b2) * 8 + 4];
-                            const float mean = mean_ordered(dsub, n, cfg.ref_device);
+#if ST_DIAG_NOEVAL
+                            const float mean = t4 / (float)__popc(cfg.reset_body_mask & 0xffffffu);
+#else
+                            const float mean = eval_mean_distance(red + slot * NB * 8 + 4, cfg.reset_body_mask, cfg.ref_device);
+#endif
                             fallen = mean > __ldg(in.term_dist + first);
                         } else {
                             fallen = t4 > 0.0f;
@@ -470,8 +525,9 @@ __global__ void __maxnreg__(ST_MAXREG) step_fused_kernel(const StepArgs a) {   /
                     float rew = ((cfg.w[0] * r0 + cfg.w[1] * r1) + cfg.w[2] * r2) + cfg.w[3] * r3;    // common.py:318-320
                     float* rr = out.reward_raw + e * out.raw_stride;
                     rr[0] = r0; rr[1] = r1; rr[2] = r2; rr[3] = r3;
+                    float pr = 0.0f;
                     if (in.dof_force) {
-                        float pr = -cfg.power_coef * t5;
+                        pr = -cfg.power_coef * t5;
                         if (cur.prog <= 3) pr = 0.0f;
                         rew = rew + pr;
                         rr[4] = pr;
@@ -480,12 +536,12 @@ __global__ void __maxnreg__(ST_MAXREG) step_fused_kernel(const StepArgs a) {   /
                     out.reward[e] = rew;
                     out.terminated[e] = fallen ? 1 : 0;
                     out.reset[e] = rst ? 1 : 0;
-                    if (out.metric_partials) {       // episode metrics (clean_pufferl/env.py:102-110): sums kept in shared memory, no registers
-                        float* m = macc + slot * 12;
-                        m[0] += 1.0f; m[1] += rew; m[2] += r0; m[3] += r1; m[4] += r2; m[5] += r3;
-                        if (in.dof_force) m[6] += rr[4];
-                        if (rst) m[7] += 1.0f;
-                        if (fallen) m[8] += 1.0f;
+                    if (!ST_DIAG_NOMETRICS && out.metric_partials) {       // episode metrics (clean_pufferl/env.py:102-110): plain stores into
+                        // this iteration's record; the WRITER warps do the summing (role A's serial tail is the kernel's critical path)
+                        float4* mm = reinterpret_cast<float4*>(meta + ((it & (ST_META - 1)) * ST_ENVS + slot) * 12);
+                        mm[0] = make_float4(1.0f, rew, r0, r1);
+                        mm[1] = make_float4(r2, r3, pr, rst ? 1.0f : 0.0f);
+                        mm[2] = make_float4(fallen ? 1.0f : 0.0f, 0.0f, 0.0f, 0.0f);
                     }
                 }
             } else if (valid) {
@@ -511,21 +567,13 @@ __global__ void __maxnreg__(ST_MAXREG) step_fused_kernel(const StepArgs a) {   /
         if (lane == 0) for (int k = 0; k < 5; ++k) g_prof[blockIdx.x][warp][k] = prof_t[k];
 #endif
         cp_async_wait_all();
-        if (role == 0 && out.metric_partials) {      // fold the slots' sums in a fixed order into this CTA's fp64 metric slot (deterministic)
-            asm volatile("bar.sync 8, %0;" ::"n"(3 * ST_GROUPS * 32) : "memory");
-            if (warp == 0 && lane < 9) {
-                float sum = 0.0f;
-#pragma unroll
-                for (int sl = 0; sl < ST_ENVS; ++sl) sum = sum + macc[sl * 12 + lane];
-                double* mp = out.metric_partials + (int64_t)blockIdx.x * PHC_NUM_METRICS + lane;
-                *mp = (out.accumulate_partials ? *mp : 0.0) + (double)sum;
-            }
-        }
     } else if (warp < ST_CWARPS + ST_WWARPS) {
         // ====================================== writer warps =======================================
         const int wtid = tid - ST_CWARPS * 32;
         const bool do_norm = out.obs_norm != nullptr;
         const bool do_mom = out.moment_partials != nullptr;
+        const bool do_met = !ST_DIAG_NOMETRICS && out.metric_partials != nullptr && wtid < 12;
+        double macc = 0.0;                  // writer thread k < 12 sums metric k over the envs of every tile, in tile / row order
         // each writer thread owns ST_WPAIRS pairs of adjacent observation columns (float2 granularity: rows are 8-byte aligned)
         float2 c_mean[ST_WPAIRS], c_inv[ST_WPAIRS];
         double msum[ST_WPAIRS][2], msq[ST_WPAIRS][2];
@@ -572,6 +620,10 @@ __global__ void __maxnreg__(ST_MAXREG) step_fused_kernel(const StepArgs a) {   /
             const int64_t e0 = blk * ST_ENVS;
             const int rows = (int)((in.N - e0 < ST_ENVS) ? (in.N - e0) : ST_ENVS);
             mbar_wait<ST_WHINT>(&full[b], (it / ST_TILES) & 1);
+            if (do_met) {
+                const float* mrec = meta + (it & (ST_META - 1)) * ST_ENVS * 12 + wtid;
+                for (int r = 0; r < rows; ++r) macc += (double)mrec[r * 12];
+            }
 #if ST_STRESS_DELAY == 3
             __nanosleep(4000 + 1000 * (it % 3));
 #endif
@@ -598,6 +650,10 @@ __global__ void __maxnreg__(ST_MAXREG) step_fused_kernel(const StepArgs a) {   /
             if (wtid == 0) mbar_arrive(&empty[b]);
         }
         if (wtid == 0) bulk_wait_all();
+        if (do_met) {                       // this CTA owns its slot: overwrite, or read-modify-write in accumulate mode (deterministic)
+            double* mp = out.metric_partials + (int64_t)blockIdx.x * PHC_NUM_METRICS + wtid;
+            *mp = (out.accumulate_partials ? *mp : 0.0) + macc;
+        }
         if (do_mom) {
             double* p = out.moment_partials + (int64_t)blockIdx.x * 2 * OBS_W;
 #pragma unroll
@@ -636,7 +692,7 @@ __global__ void __maxnreg__(ST_MAXREG) step_fused_kernel(const StepArgs a) {   /
 #endif
                 plans[d * ST_NBUF + lane] = pl;
 #if ST_PREFETCH
-                if (pl.valid) {
+                if (pl.valid & 1) {
                     if (PACKED) {
                         prefetch_l2(a.t.packed + pl.f0 * FRAME_F, FRAME_F * 4);
                         if (pl.f1 != pl.f0) prefetch_l2(a.t.packed + pl.f1 * FRAME_F, FRAME_F * 4);
@@ -651,7 +707,7 @@ __global__ void __maxnreg__(ST_MAXREG) step_fused_kernel(const StepArgs a) {   /
     }
 }
 
-constexpr size_t ST_SMEM = (size_t)(ST_TILES * ST_ENVS * OBS_W + ST_NBUF * ST_WBUF_F + ST_ENVS * NB * 8 + ST_ENVS * 24 + ST_ENVS * 12) * sizeof(float) +
+constexpr size_t ST_SMEM = (size_t)(ST_TILES * ST_ENVS * OBS_W + ST_NBUF * ST_WBUF_F + ST_ENVS * NB * 8 + ST_ENVS * 24 + ST_META * ST_ENVS * 12) * sizeof(float) +
                            ST_PLANS * ST_NBUF * sizeof(EnvPlan) +
                            (2 * ST_TILES + ST_PLANS + ST_NBUF) * sizeof(uint64_t);
 static_assert(sizeof(EnvPlan) == 48, "plan record layout");
@@ -690,27 +746,22 @@ extern "C" int phc_step_fused(const phc_motion_tables* t, const phc_step_in* in,
     }
     // the grid is fixed (one persistent CTA per SM) so that the number of moment partial slots does not depend on N
     const int grid = phc_step_num_partials();
-    StepArgs a{*t, *in, *cfg, *out, 0, 0, (in->N + ST_ENVS - 1) / ST_ENVS};
+    StepArgs a{*t, *in, *cfg, *out, 0, 0, (in->N + ST_ENVS - 1) / ST_ENVS, 0};
     a.sim_vec = aligned16(in->body_state) && (in->env_stride % 4 == 0);
     a.obs_vec = out->obs_stride == OBS_W && aligned16(out->obs) && (!out->obs_norm || aligned8(out->obs_norm));
     if (in->N == 0 && !out->moment_partials) return PHC_OK;
     cudaStream_t s = (cudaStream_t)stream;
-    static thread_local int smem_dev = -1;      // opt in to > 48 KB of dynamic shared memory once per device
-    int dev = 0;
-    cudaGetDevice(&dev);
-    if (smem_dev != dev) {
-        cudaError_t e = cudaFuncSetAttribute(step_fused_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ST_SMEM);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(step_fused_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ST_SMEM);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(step_fused_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ST_SMEM);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(step_fused_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ST_SMEM);
-        if (e != cudaSuccess) return fail((int)e, "%s: cudaFuncSetAttribute(%zu B smem): %s", fn, ST_SMEM, cudaGetErrorString(e));
-        smem_dev = dev;
-    }
     const bool dbg = out->ref_state_t || out->ref_state_t1;
-    if (packed && !dbg) step_fused_kernel<true, false><<<grid, ST_THREADS, ST_SMEM, s>>>(a);
-    else if (packed) step_fused_kernel<true, true><<<grid, ST_THREADS, ST_SMEM, s>>>(a);
-    else if (!dbg) step_fused_kernel<false, false><<<grid, ST_THREADS, ST_SMEM, s>>>(a);
-    else step_fused_kernel<false, true><<<grid, ST_THREADS, ST_SMEM, s>>>(a);
+    a.use_aux = ST_USE_AUX && packed && !dbg && !ST_TMA_LOADS && t->pair_aux && t->pair_device == cfg->ref_device &&
+                aligned16(t->pair_aux);
+    using kernel_t = void (*)(const StepArgs);
+    kernel_t k = a.use_aux ? (kernel_t)step_fused_kernel<true, false, ST_USE_AUX && !ST_TMA_LOADS>
+                 : packed ? (dbg ? (kernel_t)step_fused_kernel<true, true, false> : (kernel_t)step_fused_kernel<true, false, false>)
+                          : (dbg ? (kernel_t)step_fused_kernel<false, true, false> : (kernel_t)step_fused_kernel<false, false, false>);
+    // opt in to > 48 KB of dynamic shared memory (a per-device, per-function attribute; the call is cheap, so no cache)
+    cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ST_SMEM);
+    if (e != cudaSuccess) return fail((int)e, "%s: cudaFuncSetAttribute(%zu B smem): %s", fn, ST_SMEM, cudaGetErrorString(e));
+    k<<<grid, ST_THREADS, ST_SMEM, s>>>(a);
     return check_launch(fn);
 }
 

@@ -171,7 +171,7 @@ class FusedStep:
             self.ref_t1[row0:].data_ptr() if self.ref_t1 is not None else None,
             self.metric_partials.data_ptr() if self.metrics else None)
         with torch.cuda.device(self.device):
-            _ffi.check(self.lib.phc_step_fused(C.byref(self.motion_lib.ctables), C.byref(sin), C.byref(self._ccfg), C.byref(sout),
+            _ffi.check(self.lib.phc_step_fused(C.byref(self.motion_lib.ctables_for(self._ccfg.ref_device)), C.byref(sin), C.byref(self._ccfg), C.byref(sout),
                                                _ffi.stream_ptr()), "phc_step_fused")
             if self.defer_moments:
                 if not torch.cuda.is_current_stream_capturing():      # a capture runs no kernel: replays are counted by count_replayed()

@@ -304,7 +304,34 @@ class MotionLibBase:
     def _make_ctables(self) -> _ffi.MotionTables:
         vals = [getattr(self, _TABLE_ATTR[f]).data_ptr() for f in _ffi.TABLE_FIELDS[:-1]]
         packed = None if self.packed is None else self.packed.data_ptr()
-        return _ffi.MotionTables(*vals, packed, int(self.gts.shape[0]), self._num_motions)
+        # the pair tables of the fused step belong to the packed layout: (re)built whenever the frame tables are, for the package's
+        # current reference-device flavour; ctables_for(flavour) returns a descriptor whose pair tables match another flavour
+        self._pair = {}
+        ct = _ffi.MotionTables(*vals, packed, None, None, 0, int(self.gts.shape[0]), self._num_motions)
+        if packed is not None and self.grs.shape[1] == 24:
+            ct = self._with_pair_tables(ct, _ffi.ref_device())
+        return ct
+
+    def _with_pair_tables(self, ct: _ffi.MotionTables, flavour: int) -> _ffi.MotionTables:
+        if flavour not in self._pair:
+            F = int(self.gts.shape[0])
+            aux = torch.empty((F, 24, 2), dtype=torch.float32, device=self._device)
+            flags = torch.empty(F, dtype=torch.uint8, device=self._device)
+            with torch.cuda.device(self._device):
+                _ffi.check(self._lib.phc_build_pair_aux(C.byref(ct), flavour, _ffi.ptr(aux), _ffi.ptr(flags), _ffi.stream_ptr()),
+                           "phc_build_pair_aux")
+            self._pair[flavour] = (aux, flags)
+        aux, flags = self._pair[flavour]
+        out = _ffi.MotionTables()
+        C.memmove(C.byref(out), C.byref(ct), C.sizeof(ct))
+        out.pair_aux, out.pair_flags, out.pair_device = aux.data_ptr(), flags.data_ptr(), flavour
+        return out
+
+    def ctables_for(self, flavour: int) -> _ffi.MotionTables:
+        """The table descriptor with pair tables built for ``flavour`` (PHC_REF_DEVICE_*); built on first use, then cached."""
+        if self.packed is None or self._ctables.pair_device == flavour and self._ctables.pair_aux:
+            return self._ctables
+        return self._with_pair_tables(self._ctables, flavour)
 
     def pack(self) -> torch.Tensor:
         """Build the B200 frame layout: one contiguous 1248-byte record (gts|grs|gvs|gavs) per frame."""

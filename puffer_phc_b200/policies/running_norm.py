@@ -86,12 +86,12 @@ class RunningNorm(nn.Module):
                                                    _ffi.ptr(self.moments_buffer()), _ffi.stream_ptr()), "RunningNorm.accumulate_partials")
 
     @torch.no_grad()
-    def finalize(self, group=None) -> None:
-        """All-reduce the pending moments over ``group`` (if torch.distributed is initialised) and apply the
-        reference's running-average update; clears the pending moments."""
+    def finalize(self, group=None, allreduce: bool = True) -> None:
+        """All-reduce the pending moments over ``group`` (if torch.distributed is initialised; ``allreduce=False`` keeps the update
+        rank-local) and apply the reference's running-average update; clears the pending moments."""
         lib = _ffi.load()
         m = self.moments_buffer()
-        if torch.distributed.is_available() and torch.distributed.is_initialized() and torch.distributed.get_world_size(group) > 1:
+        if allreduce and torch.distributed.is_available() and torch.distributed.is_initialized() and torch.distributed.get_world_size(group) > 1:
             buf = self._stats if (self._stats is not None and self._moments.data_ptr() == self._stats.data_ptr()) else m
             torch.distributed.all_reduce(buf, op=torch.distributed.ReduceOp.SUM, group=group)
         C_ = self.running_mean.shape[1]

@@ -503,3 +503,34 @@ def test_deferred_moments_equal_per_step_moments(golden):
     ra.finalize(); rb.finalize()
     assert_close(npy(rb.running_mean), npy(ra.running_mean), rtol=1e-7, atol=1e-9, what="running_mean")
     assert_close(npy(rb.running_var), npy(ra.running_var), rtol=1e-7, atol=1e-12, what="running_var")
+
+
+@pytest.mark.parametrize("flavour", ["cpu", "cuda"])
+def test_pair_tables_do_not_change_the_fused_step(golden, flavour):
+    """The motion library's pair tables (slerp quantities of every frame pair, blend == 0 fast path that skips frame 1) against the
+    same kernel computing everything inline: identical outputs, bit for bit, up to the sign of exact zeros."""
+    import ctypes as C
+    from puffer_phc_b200 import _ffi, synth
+    from puffer_phc_b200.fused_step import FusedStep, StepConfig
+    from puffer_phc_b200.motion_lib import MotionLibSMPL
+    T = synth.make_motion_library(300, seed=4, device=DEV, other_fps_fraction=0.3, freeze_every=5)
+    lib = MotionLibSMPL.from_tables(T, device=DEV)
+    N = 6001
+    S = synth.make_env_state(T, N, seed=12)
+    args = [S[k] for k in ("body_state", "progress", "start_time", "start_offset", "motion_ids", "global_offset", "dof_force", "dof_vel")]
+    fs = FusedStep(lib, N, StepConfig(ref_device=flavour))
+    with_aux = {k: v.clone() for k, v in fs(*args).items()}
+    ct = lib.ctables_for(_ffi.ref_device(flavour))
+    assert ct.pair_aux and ct.pair_flags and ct.pair_device == _ffi.ref_device(flavour)
+    flags = lib._pair[_ffi.ref_device(flavour)][1]
+    assert 0 < int(flags.sum()) < flags.numel()          # frozen runs take the midpoint fall-back, the rest does not
+    plain = _ffi.MotionTables()
+    C.memmove(C.byref(plain), C.byref(ct), C.sizeof(ct))
+    plain.pair_aux, plain.pair_flags = None, None
+    lib.ctables_for = lambda flavour_: plain              # the same kernel without the tables
+    without = fs(*args)
+    torch.cuda.synchronize()
+    for k in ("obs", "reward", "reward_raw"):
+        a, b = with_aux[k] + 0.0, without[k] + 0.0         # -0.0 + 0.0 = +0.0
+        assert torch.equal(a.view(torch.int32), b.view(torch.int32)), k
+    assert torch.equal(with_aux["reset"], without["reset"]) and torch.equal(with_aux["terminated"], without["terminated"])
