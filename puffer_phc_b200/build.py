@@ -43,14 +43,16 @@ def needs_build() -> bool:
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force: bool = False, verbose: bool = False, out: str = None, extra_flags=()) -> str:
-    """``out`` / ``extra_flags``: tuning builds into another path (e.g. -DST_WHINT=200), selected at run time with PHC_B200_LIB."""
+def build(force: bool = False, verbose: bool = False, out: str = None, extra_flags=(), only=None) -> str:
+    """``out`` / ``extra_flags``: tuning builds into another path (e.g. -DST_WHINT=200), selected at run time with PHC_B200_LIB;
+    ``only``: restrict the build to these source files of csrc/ (test builds of a single kernel)."""
     target = out or LIB_PATH
     if out is None and not force and not needs_build():
         return LIB_PATH
     os.makedirs(os.path.dirname(target), exist_ok=True)
     extra = os.environ.get("PHC_NVCC_EXTRA", "").split() + list(extra_flags)      # e.g. -DST_MIN_CTAS=2 for tuning experiments
-    cmd = [_nvcc(), *NVCC_FLAGS, *extra, "-o", target, *sources()]
+    srcs = sources() if only is None else [os.path.join(CSRC, f) for f in only]
+    cmd = [_nvcc(), *NVCC_FLAGS, *extra, "-o", target, *srcs]
     if verbose:
         cmd += ["-Xptxas", "-v"]
         print(" ".join(cmd))

@@ -110,6 +110,11 @@ constexpr int ST_WBUF_F = ST_AUX_OFF + ST_AUX_F;     // per (env, role): sim rec
 #else
 #define ST_DEV(cfg) (cfg).ref_device
 #endif
+#ifndef ST_SPLIT_DONE
+#define ST_SPLIT_DONE 0                              // 1: the writers wait for role B only (role A signals on its own barrier ring);
+                                                     // bit-identical, measured 0.1683 vs 0.1677 ms: role A's lateness is not what
+                                                     // the writers wait for
+#endif
 #ifndef ST_USE_AUX
 #define ST_USE_AUX 1                                 // 0: ignore the motion library's pair tables (A/B builds)
 #endif
@@ -354,6 +359,9 @@ __global__ void __maxnreg__(ST_MAXREG) step_fused_kernel(const StepArgs a) {   /
     uint64_t* empty = bars + ST_TILES;        // [ST_TILES] tile b drained by the writers
     uint64_t* pfull = bars + 2 * ST_TILES;    // [ST_PLANS] plan set d written by the planning writer warp
     uint64_t* lfull = pfull + ST_PLANS;       // [2S] staging buffer (role, slot): bytes of the TMA bulk loads have landed
+    uint64_t* adone = lfull + ST_NBUF;        // [ST_META] role A has finished iteration it (ring slot it % ST_META): its metric record is
+                                              // written and its plan can be recycled.  Role A writes no tile rows, so the writers do
+                                              // NOT wait for it before shipping a tile (full[] counts role B only).
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const phc_step_in& in = a.in;
@@ -361,7 +369,8 @@ __global__ void __maxnreg__(ST_MAXREG) step_fused_kernel(const StepArgs a) {   /
     const phc_step_out& out = a.out;
 
     if (tid == 0) {
-        for (int i = 0; i < ST_TILES; ++i) { mbar_init(&full[i], ST_CWARPS); mbar_init(&empty[i], 1); }
+        for (int i = 0; i < ST_TILES; ++i) { mbar_init(&full[i], ST_SPLIT_DONE ? ST_CWARPS / 2 : ST_CWARPS); mbar_init(&empty[i], 1); }
+        for (int i = 0; i < ST_META; ++i) mbar_init(&adone[i], ST_CWARPS / 2);
         for (int i = 0; i < ST_PLANS; ++i) mbar_init(&pfull[i], 1);
         for (int i = 0; i < ST_NBUF; ++i) mbar_init(&lfull[i], 1);
         fence_mbar_init();
@@ -385,6 +394,7 @@ __global__ void __maxnreg__(ST_MAXREG) step_fused_kernel(const StepArgs a) {   /
         }
         cp_async_commit();
         int it = 0;
+        const float my_term_dist = __ldg(in.term_dist + j);       // this lane's body never changes
         PROF_DECL
         for (int64_t blk = blockIdx.x; blk < a.num_blocks; blk += gridDim.x, ++it) {
             const int64_t e = blk * ST_ENVS + slot;
@@ -455,6 +465,7 @@ __global__ void __maxnreg__(ST_MAXREG) step_fused_kernel(const StepArgs a) {   /
             // is still writing that older tile (the plan wait below holds role A back everywhere except in a CTA's last
             // iteration, which has no next plan).  The wait is one try_wait that succeeds at once whenever role A is the slower role.
             if ((ST_A_WAITS_TILE || role == 1) && use >= 1) mbar_wait<ST_CHINT>(&empty[b], (use - 1) & 1);
+            else if (ST_SPLIT_DONE) { if (it >= ST_META) mbar_wait<ST_CHINT>(&adone[it & (ST_META - 1)], ((it / ST_META) - 1) & 1); }
             else if (!ST_DIAG_NOFULLWAIT && use >= 1) mbar_wait<ST_CHINT>(&full[b], (use - 1) & 1);
             PROF_END(2)
 
@@ -469,7 +480,7 @@ __global__ void __maxnreg__(ST_MAXREG) step_fused_kernel(const StepArgs a) {   /
                     reward_terms_body_fma(body, ref, sp, sr, sv, sa);
                     if ((cfg.reset_body_mask >> j) & 1u) {
                         dist = norm3(body.p - ref.p, ST_DEV(cfg));
-                        if (!cfg.use_mean) dist = (dist > __ldg(in.term_dist + j)) ? 1.0f : 0.0f;     // common.py:347-350 (any)
+                        if (!cfg.use_mean) dist = (dist > my_term_dist) ? 1.0f : 0.0f;                // common.py:347-350 (any)
                     }
                     *reinterpret_cast<float4*>(rj) = make_float4(sp, sr, sv, sa);
                     *reinterpret_cast<float2*>(rj + 4) = make_float2(dist, power);
@@ -557,9 +568,14 @@ __global__ void __maxnreg__(ST_MAXREG) step_fused_kernel(const StepArgs a) {   /
                 task_obs_body_fma(body, ref, root_p, hz, hw, hrot, q + 3 * j, q + 72 + 6 * j, q + 216 + 3 * j, q + 288 + 3 * j,
                                   q + 360 + 3 * j, q + 432 + 6 * j);
             }
-            fence_proxy_async();            // tile rows were written by ordinary stores; the writers read them through TMA
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&full[b]);
+            if (ST_SPLIT_DONE && role == 0) {
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&adone[it & (ST_META - 1)]);
+            } else {
+                fence_proxy_async();        // tile rows were written by ordinary stores; the writers read them through TMA
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&full[b]);
+            }
             cur = nxt;
         }
 #if ST_PROFILE
@@ -620,10 +636,12 @@ __global__ void __maxnreg__(ST_MAXREG) step_fused_kernel(const StepArgs a) {   /
             const int64_t e0 = blk * ST_ENVS;
             const int rows = (int)((in.N - e0 < ST_ENVS) ? (in.N - e0) : ST_ENVS);
             mbar_wait<ST_WHINT>(&full[b], (it / ST_TILES) & 1);
+#if !ST_SPLIT_DONE
             if (do_met) {
                 const float* mrec = meta + (it & (ST_META - 1)) * ST_ENVS * 12 + wtid;
                 for (int r = 0; r < rows; ++r) macc += (double)mrec[r * 12];
             }
+#endif
 #if ST_STRESS_DELAY == 3
             __nanosleep(4000 + 1000 * (it % 3));
 #endif
@@ -648,6 +666,13 @@ __global__ void __maxnreg__(ST_MAXREG) step_fused_kernel(const StepArgs a) {   /
             if (bulk && wtid == 0) bulk_wait_read();     // the TMA engine has finished reading the tile from shared memory
             writers_sync();
             if (wtid == 0) mbar_arrive(&empty[b]);
+#if ST_SPLIT_DONE
+            if (do_met) {                                // role A's record of this iteration (it is rarely still missing by now)
+                mbar_wait<ST_WHINT>(&adone[it & (ST_META - 1)], (it / ST_META) & 1);
+                const float* mrec = meta + (it & (ST_META - 1)) * ST_ENVS * 12 + wtid;
+                for (int r = 0; r < rows; ++r) macc += (double)mrec[r * 12];
+            }
+#endif
         }
         if (wtid == 0) bulk_wait_all();
         if (do_met) {                       // this CTA owns its slot: overwrite, or read-modify-write in accumulate mode (deterministic)
@@ -683,6 +708,7 @@ __global__ void __maxnreg__(ST_MAXREG) step_fused_kernel(const StepArgs a) {   /
             if (p >= ST_PLANS - 1) {
                 const int q = p - (ST_PLANS - 1);
                 mbar_wait<ST_WHINT>(&full[q % ST_TILES], (q / ST_TILES) & 1);
+                if (ST_SPLIT_DONE) mbar_wait<ST_WHINT>(&adone[q & (ST_META - 1)], (q / ST_META) & 1);
             }
             const int d = p % ST_PLANS;
             if (lane < ST_NBUF) {
@@ -709,7 +735,7 @@ __global__ void __maxnreg__(ST_MAXREG) step_fused_kernel(const StepArgs a) {   /
 
 constexpr size_t ST_SMEM = (size_t)(ST_TILES * ST_ENVS * OBS_W + ST_NBUF * ST_WBUF_F + ST_ENVS * NB * 8 + ST_ENVS * 24 + ST_META * ST_ENVS * 12) * sizeof(float) +
                            ST_PLANS * ST_NBUF * sizeof(EnvPlan) +
-                           (2 * ST_TILES + ST_PLANS + ST_NBUF) * sizeof(uint64_t);
+                           (2 * ST_TILES + ST_PLANS + ST_NBUF + ST_META) * sizeof(uint64_t);
 static_assert(sizeof(EnvPlan) == 48, "plan record layout");
 static_assert(ST_SMEM <= 227 * 1024, "shared memory budget");
 
