@@ -267,6 +267,15 @@ int phc_amp_obs_smpl(const float *root_pos, const float *root_rot, const float *
                      int num_joints, int K, int local_root_obs, int root_height_obs, int upright, int64_t N, float *obs,
                      int64_t obs_stride, int ref_device, phc_stream_t stream);
 
+/* The AMP observation step of HumanoidPHC.step (humanoid_phc.py:154-157) on the history buffer _amp_obs_buf [N, num_steps, row_width]
+ * (:600-606): _update_hist_amp_obs (:1339-1348: rows 1.. = old rows 0..num_steps-2) and _compute_amp_observations (:1123-1174: row 0 =
+ * the current observation) in ONE pass -- the reference clones the buffer, copies it back shifted, computes the row and copies it in.
+ * Same arguments as phc_amp_obs_smpl; 2 <= num_steps <= 16; row_width >= the kernel's row (pass-through columns stay the caller's). */
+int phc_amp_obs_hist_step(const float *root_pos, const float *root_rot, const float *root_vel, const float *root_ang_vel,
+                          const float *dof_pos, const float *dof_vel, const float *key_body_pos, const int64_t *dof_subset,
+                          int num_joints, int K, int local_root_obs, int root_height_obs, int upright, int64_t N,
+                          float *amp_obs_buf, int num_steps, int row_width, int ref_device, phc_stream_t stream);
+
 /* ------------------------------------------------------------------------------------------- */
 /* The whole post-physics half of HumanoidPHC.step in ONE pass over HBM                          */
 /* (puffer_phc/envs/humanoid_phc.py:136-149: _compute_reward :1228-1303, _compute_reset          */

@@ -13,4 +13,17 @@ All arithmetic runs in hand-written CUDA kernels behind the C-ABI library ``libp
 """
 from ._ffi import set_reference_device  # noqa: E402,F401  ("cuda" default | "cpu": whose torch rounding flags reproduce)
 
-__version__ = "0.1.1"
+
+
+def install_c_gae_shim() -> str:
+    """Put ``puffer_phc_b200/shims`` at the front of ``sys.path`` so that the reference's ``from c_gae import compute_gae``
+    (reference puffer_phc/clean_pufferl/core.py:36) imports the CUDA-backed drop-in without an edit.  Returns the directory."""
+    import os
+    import sys
+    d = os.path.join(os.path.dirname(os.path.abspath(__file__)), "shims")
+    if d not in sys.path:
+        sys.path.insert(0, d)
+    return d
+
+
+__version__ = "0.1.2"

@@ -18,7 +18,7 @@ c_f32p, c_i64p, c_u8p, c_i16p, c_f64p = C.c_void_p, C.c_void_p, C.c_void_p, C.c_
 
 EXPORTS = (
     "phc_version", "phc_last_error", "phc_pack_frames", "phc_build_pair_aux", "phc_motion_state", "phc_reset_ref_state", "phc_sample_time_interval",
-    "phc_imitation_obs_v6", "phc_self_obs_smpl_max", "phc_amp_obs_smpl", "phc_imitation_reward", "phc_im_reset",
+    "phc_imitation_obs_v6", "phc_self_obs_smpl_max", "phc_amp_obs_smpl", "phc_amp_obs_hist_step", "phc_imitation_reward", "phc_im_reset",
     "phc_step_num_partials", "phc_step_fused", "phc_rms_forward", "phc_rms_scratch_doubles", "phc_rms_moments",
     "phc_rms_reduce_partials", "phc_rms_finalize", "phc_auto_reset_num_partials", "phc_auto_reset_scratch_bytes", "phc_auto_reset",
     "phc_stats_reduce", "phc_gae", "phc_build_motion_tables", "phc_build_motion_aa", "phc_cast_f64_f32", "phc_mpjpe", "phc_frame_blend",
@@ -123,6 +123,7 @@ def _declare(lib):
     lib.phc_imitation_obs_v6.argtypes = [View] * 10 + [I64, I, I, I, P, I64, P]
     lib.phc_self_obs_smpl_max.argtypes = [View] * 4 + [I64, I, I, I, I, P, I64, P]
     lib.phc_amp_obs_smpl.argtypes = [P] * 8 + [I, I, I, I, I, I64, P, I64, I, P]
+    lib.phc_amp_obs_hist_step.argtypes = [P] * 8 + [I, I, I, I, I, I64, P, I, I, I, P]
     lib.phc_imitation_reward.argtypes = [View] * 8 + [I64, I, C.POINTER(F), C.POINTER(F), P, P, I64, P]
     lib.phc_im_reset.argtypes = [P, View, View, P, I, P, I, I64, I, P, P, I, P]
     lib.phc_step_num_partials.argtypes, lib.phc_step_num_partials.restype = [], I
@@ -229,6 +230,27 @@ def require_cuda(*tensors):
         if t is not None and not t.is_cuda:
             raise RuntimeError("puffer_phc_b200: expected CUDA tensors -- the kernels are the only implementation "
                                f"(got a tensor on {t.device})")
+
+
+class _NullCtx:
+    def __enter__(self):
+        return None
+
+    def __exit__(self, *a):
+        return False
+
+
+_NULL = _NullCtx()
+
+
+def on_device(dev):
+    """Context that makes ``dev`` the current CUDA device for the launch -- a no-op object when it already is (the usual case:
+    ``torch.cuda.device(...)`` alone costs several microseconds per call, more than a 4096-env kernel runs)."""
+    import torch
+    if not isinstance(dev, torch.device):
+        dev = torch.device(dev)
+    idx = dev.index if dev.index is not None else torch.cuda.current_device()
+    return _NULL if idx == torch.cuda.current_device() else torch.cuda.device(idx)
 
 
 def stream_ptr():

@@ -23,7 +23,7 @@ def compute_gae_cuda(dones: torch.Tensor, values: torch.Tensor, rewards: torch.T
     if not (d.numel() == L and v.numel() == L):
         raise ValueError("compute_gae: dones, values and rewards must have the same length")
     adv = torch.empty(L, dtype=torch.float32, device=r.device) if out is None else out
-    with torch.cuda.device(r.device):
+    with _ffi.on_device(r.device):
         _ffi.check(lib.phc_gae(_ffi.ptr(d), _ffi.ptr(v), _ffi.ptr(r), L, float(gamma), float(gae_lambda), _ffi.ptr(adv), int(mode),
                                _ffi.stream_ptr()), "compute_gae")
     return adv

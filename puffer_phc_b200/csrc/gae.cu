@@ -27,14 +27,15 @@ constexpr int GAE_KMAX = 2048;
 // one padding word per CH elements: thread t starts at (CH+1)*t, and CH+1 is odd, so a warp hits 32 distinct banks
 template <int CH> __device__ __forceinline__ int padc(int i) { return i + i / CH; }
 
-// GAE_CH = elements owned by a thread.  8 for short warm-up windows (4x more threads: the kernel is latency-bound at
-// rollout sizes), 32 when the window is long (keeps the redundant warm-up work at K/32 per element).
-template <int GAE_CH>
-__global__ void __launch_bounds__(GAE_THREADS) gae_blocked_kernel(const float* __restrict__ dones, const float* __restrict__ values,
-                                                                  const float* __restrict__ rewards, int64_t L, float gamma,
-                                                                  float gl, int K, float* __restrict__ adv) {
+// GAE_CH = elements owned by a thread, THREADS = threads per CTA.  CH = 8 for short warm-up windows (the kernel is latency-bound at
+// rollout sizes: many short chains), 32 when the window is long (keeps the redundant warm-up work at K/32 per element).  Tiles are
+// staged with 16-byte loads when the three arrays allow it (tile starts are multiples of 4 elements).
+template <int GAE_CH, int THREADS>
+__global__ void __launch_bounds__(THREADS) gae_blocked_kernel(const float* __restrict__ dones, const float* __restrict__ values,
+                                                              const float* __restrict__ rewards, int64_t L, float gamma,
+                                                              float gl, int K, float* __restrict__ adv, int vec) {
     extern __shared__ float sm[];
-    constexpr int GAE_TILE = GAE_CH * GAE_THREADS;
+    constexpr int GAE_TILE = GAE_CH * THREADS;
     const int span = GAE_TILE + K + 1;                 // elements [tile0, tile0 + span) are needed
     const int pspan = padc<GAE_CH>(span) + 1;
     float* s_d = sm;
@@ -43,14 +44,26 @@ __global__ void __launch_bounds__(GAE_THREADS) gae_blocked_kernel(const float* _
     float* s_a = s_r + pspan;                          // [padc<GAE_CH>(GAE_TILE)+1]
     const int64_t tile0 = (int64_t)blockIdx.x * GAE_TILE;
     const int64_t avail = (L - tile0 < span) ? (L - tile0) : span;
-    for (int i = threadIdx.x; i < avail; i += GAE_THREADS) {
+    const int n4 = vec ? (int)(avail >> 2) : 0;
+    const float4* d4 = reinterpret_cast<const float4*>(dones + tile0);
+    const float4* v4 = reinterpret_cast<const float4*>(values + tile0);
+    const float4* r4 = reinterpret_cast<const float4*>(rewards + tile0);
+    for (int q = threadIdx.x; q < n4; q += THREADS) {
+        const float4 a = __ldg(d4 + q), b = __ldg(v4 + q), c = __ldg(r4 + q);
+        const int i = 4 * q;
+        const int p0 = padc<GAE_CH>(i), p1 = padc<GAE_CH>(i + 1), p2 = padc<GAE_CH>(i + 2), p3 = padc<GAE_CH>(i + 3);
+        s_d[p0] = a.x; s_d[p1] = a.y; s_d[p2] = a.z; s_d[p3] = a.w;
+        s_v[p0] = b.x; s_v[p1] = b.y; s_v[p2] = b.z; s_v[p3] = b.w;
+        s_r[p0] = c.x; s_r[p1] = c.y; s_r[p2] = c.z; s_r[p3] = c.w;
+    }
+    for (int i = 4 * n4 + threadIdx.x; i < avail; i += THREADS) {
         const int p = padc<GAE_CH>(i);
         s_d[p] = __ldg(dones + tile0 + i);
         s_v[p] = __ldg(values + tile0 + i);
         s_r[p] = __ldg(rewards + tile0 + i);
     }
     __syncthreads();
-    const int c0 = threadIdx.x * GAE_CH;               // chunk [c0, c0+32) relative to the tile
+    const int c0 = threadIdx.x * GAE_CH;               // chunk [c0, c0 + CH) relative to the tile
     if (tile0 + c0 < L) {
         // highest t_cur this thread evaluates: warm-up start, clipped to L-2 (adv[L-1] = 0 starts the true scan)
         int64_t hi = tile0 + c0 + GAE_CH - 1 + K;
@@ -67,7 +80,15 @@ __global__ void __launch_bounds__(GAE_THREADS) gae_blocked_kernel(const float* _
     }
     __syncthreads();
     const int64_t nout = (L - tile0 < GAE_TILE) ? (L - tile0) : GAE_TILE;
-    for (int i = threadIdx.x; i < nout; i += GAE_THREADS) adv[tile0 + i] = s_a[padc<GAE_CH>(i)];
+    if (vec && (nout & 3) == 0) {
+        float4* o4 = reinterpret_cast<float4*>(adv + tile0);
+        for (int q = threadIdx.x; q < (int)(nout >> 2); q += THREADS) {
+            const int i = 4 * q;
+            o4[q] = make_float4(s_a[padc<GAE_CH>(i)], s_a[padc<GAE_CH>(i + 1)], s_a[padc<GAE_CH>(i + 2)], s_a[padc<GAE_CH>(i + 3)]);
+        }
+    } else {
+        for (int i = threadIdx.x; i < nout; i += THREADS) adv[tile0 + i] = s_a[padc<GAE_CH>(i)];
+    }
 }
 
 // one warp: coalesced staging of 1024-element chunks, lane 0 runs the recurrence.
@@ -130,18 +151,27 @@ extern "C" int phc_gae(const float* dones, const float* values, const float* rew
         return check_launch(fn);
     }
     const int ch = (K <= 64) ? 8 : 32;
-    const int tile = ch * GAE_THREADS;
+#ifndef GAE_T8
+#define GAE_T8 256                                     // threads per CTA of the CH = 8 instantiation (A/B: 64 / 128 / 256)
+#endif
+    const int threads = ch == 8 ? GAE_T8 : GAE_THREADS;
+    const int tile = ch * threads;
     const int span = tile + K + 1;
     const size_t smem = (size_t)(3 * ((span + span / ch) + 1) + (tile + tile / ch) + 1) * sizeof(float);
     const int64_t tiles = (L + tile - 1) / tile;
+    const int vec = aligned16(dones) && aligned16(values) && aligned16(rewards) && aligned16(advantages);
     if (ch == 8) {
-        gae_blocked_kernel<8><<<(unsigned)tiles, GAE_THREADS, smem, s>>>(dones, values, rewards, L, gamma, gl, K, advantages);
-    } else {
-        if (smem > 48 * 1024) {      // per-device attribute and a cheap call: set it on every launch that needs it (no per-thread cache)
-            cudaError_t e = cudaFuncSetAttribute(gae_blocked_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (smem > 48 * 1024) {
+            cudaError_t e = cudaFuncSetAttribute(gae_blocked_kernel<8, GAE_T8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
             if (e != cudaSuccess) return fail((int)e, "%s: cudaFuncSetAttribute: %s", fn, cudaGetErrorString(e));
         }
-        gae_blocked_kernel<32><<<(unsigned)tiles, GAE_THREADS, smem, s>>>(dones, values, rewards, L, gamma, gl, K, advantages);
+        gae_blocked_kernel<8, GAE_T8><<<(unsigned)tiles, GAE_T8, smem, s>>>(dones, values, rewards, L, gamma, gl, K, advantages, vec);
+    } else {
+        if (smem > 48 * 1024) {      // per-device attribute and a cheap call: set it on every launch that needs it (no per-thread cache)
+            cudaError_t e = cudaFuncSetAttribute(gae_blocked_kernel<32, GAE_THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e != cudaSuccess) return fail((int)e, "%s: cudaFuncSetAttribute: %s", fn, cudaGetErrorString(e));
+        }
+        gae_blocked_kernel<32, GAE_THREADS><<<(unsigned)tiles, GAE_THREADS, smem, s>>>(dones, values, rewards, L, gamma, gl, K, advantages, vec);
     }
     return check_launch(fn);
 }

@@ -183,12 +183,32 @@ __global__ void __launch_bounds__(IM_WARPS * 32) mpjpe_kernel(const MpjpeArgs a)
 struct AmpArgs {
     const float *root_pos, *root_rot, *root_vel, *root_ang, *dof_pos, *dof_vel, *key_pos;
     const int64_t* subset; int nj, K, local_root_obs, root_height_obs, upright; int64_t N; float* obs; int64_t obs_stride; int dev;
+    int hist, hist_w;      // history variant: rows per env and floats per row
 };
 
+// HIST > 0: obs is the history buffer _amp_obs_buf [N, HIST, W] (row stride obs_stride / HIST): the warp first shifts the env's rows
+// one step back in place (_update_hist_amp_obs, humanoid_phc.py:1339-1348: hist[:, k] = buf[:, k-1]; a lane owns a column, so
+// walking the rows from the oldest to the newest needs no synchronisation), then writes the current observation into row 0
+// (_compute_amp_observations, :1123-1174) -- one pass instead of clone + copy + compute + copy.
+template <bool HISTORY>
 __global__ void __launch_bounds__(IM_WARPS * 32) amp_obs_kernel(const AmpArgs a) {
     const int lane = threadIdx.x & 31;
     const int64_t n = (int64_t)blockIdx.x * IM_WARPS + (threadIdx.x >> 5);
     if (n >= a.N) return;
+    if (HISTORY) {
+        float* buf = a.obs + n * a.obs_stride;
+        const int W = a.hist_w;
+        for (int c = lane; c < W; c += 32) {      // all loads of a column first (independent, in flight together), then the stores
+            float v[15];
+#pragma unroll
+            for (int k = 0; k < 15; ++k)
+                if (k < a.hist - 1) v[k] = buf[k * W + c];
+#pragma unroll
+            for (int k = 0; k < 15; ++k)
+                if (k < a.hist - 1) buf[(k + 1) * W + c] = v[k];
+        }
+        __syncwarp();
+    }
     Q4 rr = ld4(a.root_rot + n * 4);
     if (!a.upright) rr = remove_base_rot(rr);                                   // common.py:214-215
     float hz, hw;
@@ -286,8 +306,26 @@ extern "C" int phc_amp_obs_smpl(const float* root_pos, const float* root_rot, co
                 "%s: NULL pointer", fn);
     PHC_REQUIRE(obs_stride >= (root_height_obs ? 1 : 0) + 12 + 9 * num_joints + 3 * K, PHC_ESHAPE, "%s: obs_stride too small", fn);
     AmpArgs a{root_pos, root_rot, root_vel, root_ang_vel, dof_pos, dof_vel, key_body_pos, dof_subset, num_joints, K, local_root_obs,
-              root_height_obs, upright, N, obs, obs_stride, ref_device};
-    amp_obs_kernel<<<(unsigned)((N + IM_WARPS - 1) / IM_WARPS), IM_WARPS * 32, 0, (cudaStream_t)stream>>>(a);
+              root_height_obs, upright, N, obs, obs_stride, ref_device, 0, 0};
+    amp_obs_kernel<false><<<(unsigned)((N + IM_WARPS - 1) / IM_WARPS), IM_WARPS * 32, 0, (cudaStream_t)stream>>>(a);
+    return check_launch(fn);
+}
+
+extern "C" int phc_amp_obs_hist_step(const float* root_pos, const float* root_rot, const float* root_vel, const float* root_ang_vel,
+                                     const float* dof_pos, const float* dof_vel, const float* key_body_pos, const int64_t* dof_subset,
+                                     int num_joints, int K, int local_root_obs, int root_height_obs, int upright, int64_t N,
+                                     float* amp_obs_buf, int num_steps, int row_width, int ref_device, phc_stream_t stream) {
+    const char* fn = "phc_amp_obs_hist_step";
+    PHC_REQUIRE(N >= 0, PHC_EINVAL, "%s: N < 0", fn);
+    PHC_REQUIRE(num_joints >= 0 && num_joints <= 23 && K >= 0, PHC_ESHAPE, "%s: num_joints=%d K=%d out of range", fn, num_joints, K);
+    PHC_REQUIRE(num_steps >= 2 && num_steps <= 16, PHC_ESHAPE, "%s: num_steps=%d outside [2,16]", fn, num_steps);
+    if (N == 0) return PHC_OK;
+    PHC_REQUIRE(root_pos && root_rot && root_vel && root_ang_vel && dof_pos && dof_vel && (key_body_pos || K == 0) && amp_obs_buf, PHC_EINVAL,
+                "%s: NULL pointer", fn);
+    PHC_REQUIRE(row_width >= (root_height_obs ? 1 : 0) + 12 + 9 * num_joints + 3 * K, PHC_ESHAPE, "%s: row_width too small", fn);
+    AmpArgs a{root_pos, root_rot, root_vel, root_ang_vel, dof_pos, dof_vel, key_body_pos, dof_subset, num_joints, K, local_root_obs,
+              root_height_obs, upright, N, amp_obs_buf, (int64_t)num_steps * row_width, ref_device, num_steps, row_width};
+    amp_obs_kernel<true><<<(unsigned)((N + IM_WARPS - 1) / IM_WARPS), IM_WARPS * 32, 0, (cudaStream_t)stream>>>(a);
     return check_launch(fn);
 }
 

@@ -23,14 +23,15 @@ def _prep(*ts):
 
 
 def compute_imitation_observations_v6(root_pos, root_rot, body_pos, body_rot, body_vel, body_ang_vel, ref_body_pos,
-                                      ref_body_rot, ref_body_vel, ref_body_ang_vel, time_steps: int, upright: bool):
-    """reference envs/common.py:106-176 -> ``[B, J*24]`` (six body-major blocks 3J|6J|3J|3J|3J|6J)."""
+                                      ref_body_rot, ref_body_vel, ref_body_ang_vel, time_steps: int, upright: bool, out=None):
+    """reference envs/common.py:106-176 -> ``[B, J*24]`` (six body-major blocks 3J|6J|3J|3J|3J|6J).  ``out`` (optional, beyond the
+    reference's signature): a ``[B, >= J*24]`` float32 buffer with unit inner stride to write into instead of allocating."""
     lib = _ffi.load()
     ts = _prep(root_pos, root_rot, body_pos, body_rot, body_vel, body_ang_vel, ref_body_pos, ref_body_rot, ref_body_vel,
                ref_body_ang_vel)
     B, J = ts[2].shape[0], ts[2].shape[1]
-    obs = torch.empty((B, 24 * J), dtype=torch.float32, device=ts[2].device)
-    with torch.cuda.device(obs.device):
+    obs = torch.empty((B, 24 * J), dtype=torch.float32, device=ts[2].device) if out is None else out
+    with _ffi.on_device(obs.device):
         _ffi.check(lib.phc_imitation_obs_v6(*[_ffi.view3(t) for t in ts], B, J, int(time_steps), int(bool(upright)),
                                             _ffi.ptr(obs), obs.stride(0), _ffi.stream_ptr()), "compute_imitation_observations_v6")
     return obs
@@ -50,7 +51,7 @@ def compute_humanoid_observations_smpl_max(body_pos, body_rot, body_vel, body_an
         extra.append(limb_weight_params)
     Wt = W + sum(int(x.shape[-1]) for x in extra)
     obs = torch.empty((B, Wt), dtype=torch.float32, device=ts[0].device)
-    with torch.cuda.device(obs.device):
+    with _ffi.on_device(obs.device):
         _ffi.check(lib.phc_self_obs_smpl_max(*[_ffi.view3(t) for t in ts], B, J, int(bool(local_root_obs)),
                                              int(bool(root_height_obs)), int(bool(upright)), _ffi.ptr(obs), obs.stride(0),
                                              _ffi.stream_ptr()), "compute_humanoid_observations_smpl_max")
@@ -104,7 +105,7 @@ def build_amp_observations_smpl(root_pos, root_rot, root_vel, root_ang_vel, dof_
         extra.append(limb_weight_params)
     Wt = W + sum(int(x.shape[-1]) for x in extra)
     obs = torch.empty((B, Wt), dtype=torch.float32, device=ts[0].device)
-    with torch.cuda.device(obs.device):
+    with _ffi.on_device(obs.device):
         _ffi.check(lib.phc_amp_obs_smpl(*[_ffi.ptr(t) for t in ts], _ffi.ptr(sub), nj, K, int(bool(local_root_obs)),
                                         int(bool(root_height_obs)), int(bool(upright)), B, _ffi.ptr(obs), obs.stride(0),
                                         _ffi.ref_device(), _ffi.stream_ptr()), "build_amp_observations_smpl")
@@ -115,18 +116,54 @@ def build_amp_observations_smpl(root_pos, root_rot, root_vel, root_ang_vel, dof_
     return obs
 
 
+def amp_obs_history_step(amp_obs_buf, root_pos, root_rot, root_vel, root_ang_vel, dof_pos, dof_vel, key_body_pos, shape_params,
+                         limb_weight_params, dof_subset, local_root_obs, root_height_obs, has_dof_subset, has_shape_obs_disc,
+                         has_limb_weight_obs, upright):
+    """``HumanoidPHC._update_hist_amp_obs()`` followed by ``_compute_amp_observations()`` (reference puffer_phc/envs/humanoid_phc.py:
+    154-157, 1123-1174, 1339-1348) on ``amp_obs_buf [N, num_amp_obs_steps, num_amp_obs_per_step]`` IN PLACE, in one kernel: every
+    env's rows move one step back and row 0 receives the current observation (same arguments as ``build_amp_observations_smpl``)."""
+    lib = _ffi.load()
+    _ffi.require_cuda(amp_obs_buf, root_pos, root_rot, root_vel, root_ang_vel, dof_pos, dof_vel, key_body_pos)
+    if amp_obs_buf.dim() != 3 or not amp_obs_buf.is_contiguous() or amp_obs_buf.dtype != torch.float32:
+        raise TypeError("amp_obs_buf must be a contiguous float32 [N, steps, width] tensor (it is updated in place)")
+    ts = [t.to(torch.float32).contiguous() for t in (root_pos, root_rot, root_vel, root_ang_vel, dof_pos, dof_vel, key_body_pos)]
+    B, S, Wt = amp_obs_buf.shape
+    K = ts[6].shape[1]
+    sub, nj = None, 23
+    if has_dof_subset:
+        sub = dof_subset.to(device=ts[0].device, dtype=torch.int64).contiguous()
+        nj = sub.numel() // 3
+    W = (1 if root_height_obs else 0) + 12 + 9 * nj + 3 * K
+    extra = ([shape_params] if has_shape_obs_disc else []) + ([limb_weight_params] if has_limb_weight_obs else [])
+    if Wt != W + sum(int(x.shape[-1]) for x in extra):
+        raise ValueError(f"amp_obs_buf rows are {Wt} wide, the observation is {W + sum(int(x.shape[-1]) for x in extra)}")
+    with _ffi.on_device(amp_obs_buf.device):
+        _ffi.check(lib.phc_amp_obs_hist_step(*[_ffi.ptr(t) for t in ts], _ffi.ptr(sub), nj, K, int(bool(local_root_obs)),
+                                             int(bool(root_height_obs)), int(bool(upright)), B, _ffi.ptr(amp_obs_buf), S, Wt,
+                                             _ffi.ref_device(), _ffi.stream_ptr()), "amp_obs_history_step")
+    col = W
+    for x in extra:                                   # plain pass-through columns of the current row (common.py:253-266)
+        amp_obs_buf[:, 0, col:col + x.shape[-1]] = x
+        col += x.shape[-1]
+    return amp_obs_buf
+
+
 def compute_imitation_reward(root_pos, root_rot, body_pos, body_rot, body_vel, body_ang_vel, ref_body_pos, ref_body_rot,
-                             ref_body_vel, ref_body_ang_vel, rwd_specs: Dict[str, float]) -> Tuple[torch.Tensor, torch.Tensor]:
-    """reference envs/common.py:270-322 -> ``(reward [B], reward_raw [B,4])``.  root_pos/root_rot are unused there too."""
+                             ref_body_vel, ref_body_ang_vel, rwd_specs: Dict[str, float], out=None) -> Tuple[torch.Tensor, torch.Tensor]:
+    """reference envs/common.py:270-322 -> ``(reward [B], reward_raw [B,4])``.  root_pos/root_rot are unused there too.
+    ``out`` (optional): ``(reward, reward_raw)`` buffers to write into."""
     lib = _ffi.load()
     ts = _prep(body_pos, body_rot, body_vel, body_ang_vel, ref_body_pos, ref_body_rot, ref_body_vel, ref_body_ang_vel)
     B, J = ts[0].shape[0], ts[0].shape[1]
     k = (C.c_float * 4)(*[float(rwd_specs[n]) for n in _KEYS_K])
     w = (C.c_float * 4)(*[float(rwd_specs[n]) for n in _KEYS_W])
-    reward = torch.empty(B, dtype=torch.float32, device=ts[0].device)
-    raw = torch.empty((B, 4), dtype=torch.float32, device=ts[0].device)
-    with torch.cuda.device(reward.device):
-        _ffi.check(lib.phc_imitation_reward(*[_ffi.view3(t) for t in ts], B, J, k, w, _ffi.ptr(reward), _ffi.ptr(raw), 4,
+    if out is None:
+        reward = torch.empty(B, dtype=torch.float32, device=ts[0].device)
+        raw = torch.empty((B, 4), dtype=torch.float32, device=ts[0].device)
+    else:
+        reward, raw = out
+    with _ffi.on_device(reward.device):
+        _ffi.check(lib.phc_imitation_reward(*[_ffi.view3(t) for t in ts], B, J, k, w, _ffi.ptr(reward), _ffi.ptr(raw), raw.stride(0),
                                             _ffi.stream_ptr()), "compute_imitation_reward")
     return reward, raw
 
@@ -146,7 +183,7 @@ def compute_humanoid_im_reset(reset_buf, progress_buf, contact_buf, contact_body
         td = td.expand(J).contiguous()
     reset = torch.empty(B, dtype=torch.bool, device=pos.device)
     term = torch.empty(B, dtype=torch.bool, device=pos.device)
-    with torch.cuda.device(pos.device):
+    with _ffi.on_device(pos.device):
         _ffi.check(lib.phc_im_reset(_ffi.ptr(prog), _ffi.view3(pos), _ffi.view3(ref), _ffi.ptr(pt), int(bool(enable_early_termination)),
                                     _ffi.ptr(td), int(bool(use_mean)), B, J, _ffi.ptr(reset), _ffi.ptr(term), _ffi.ref_device(),
                                     _ffi.stream_ptr()),
@@ -163,7 +200,7 @@ def compute_mpjpe(rigid_body_pos, ref_body_pos):
     pos, ref = _prep(rigid_body_pos, ref_body_pos)
     B, J = pos.shape[0], pos.shape[1]
     out = torch.empty(B, dtype=torch.float32, device=pos.device)
-    with torch.cuda.device(pos.device):
+    with _ffi.on_device(pos.device):
         _ffi.check(lib.phc_mpjpe(_ffi.view3(pos), _ffi.view3(ref), B, J, _ffi.ptr(out), _ffi.ref_device(), _ffi.stream_ptr()),
                    "compute_mpjpe")
     return out

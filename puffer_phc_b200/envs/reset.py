@@ -62,7 +62,7 @@ def reset_envs(env: EnvTensors, motion_lib, env_ids: torch.Tensor, random_start:
     bs = env.rigid_body_state
     assert bs.is_contiguous() and env.humanoid_root_states.is_contiguous() and env.dof_pos.is_contiguous() and env.dof_vel.is_contiguous()
     # _sample_ref_state query (offset = the envs' CURRENT global offset, :859-861) + _set_env_state (:899-929)
-    with torch.cuda.device(bs.device):
+    with _ffi.on_device(bs.device):
         _ffi.check(lib.phc_reset_ref_state(C.byref(motion_lib.ctables), _ffi.ptr(env_ids), _ffi.ptr(env.sampled_motion_ids),
                                            _ffi.ptr(motion_times), _ffi.ptr(env.global_offset), env_ids.shape[0],
                                            _ffi.ptr(env.humanoid_root_states), _ffi.ptr(env.dof_pos), _ffi.ptr(env.dof_vel), _ffi.ptr(bs),
@@ -195,7 +195,7 @@ class AutoReset:
                               1 if self.step_metrics else 0)
         f = self.fused
         mom = f is not None and f.accumulate_moments
-        with torch.cuda.device(self.device):
+        with _ffi.on_device(self.device):
             _ffi.check(self.lib.phc_auto_reset(C.byref(self.motion_lib.ctables), C.byref(self._cenv), C.byref(book), C.byref(self._ccfg),
                                                _ffi.ptr(phase), N, _ffi.ptr(self.reset_ids), _ffi.ptr(self.reset_count), _ffi.ptr(self._scratch),
                                                f.partials[f.num_partials:].data_ptr() if mom else None,

@@ -170,7 +170,7 @@ class FusedStep:
             self.ref_t[row0:].data_ptr() if self.ref_t is not None else None,
             self.ref_t1[row0:].data_ptr() if self.ref_t1 is not None else None,
             self.metric_partials.data_ptr() if self.metrics else None)
-        with torch.cuda.device(self.device):
+        with _ffi.on_device(self.device):
             _ffi.check(self.lib.phc_step_fused(C.byref(self.motion_lib.ctables_for(self._ccfg.ref_device)), C.byref(sin), C.byref(self._ccfg), C.byref(sout),
                                                _ffi.stream_ptr()), "phc_step_fused")
             if self.defer_moments:
@@ -201,7 +201,7 @@ class FusedStep:
         """``defer_moments`` mode: fold the sums the kernel has accumulated since the last flush (moments, the auto-reset tail's
         corrections and the episode metrics) into ``self.stats`` and clear the per-CTA slots -- ONE launch."""
         if self.defer_moments and self._pending_rows:
-            with torch.cuda.device(self.device):
+            with _ffi.on_device(self.device):
                 self._reduce(self._pending_rows, zero=True)
             self._pending_rows = 0
 

@@ -215,7 +215,7 @@ class MotionLibBase:
                           len(first), int(tiles[-1]), J)
         bo = _ffi.BuildOut(*[t.data_ptr() for t in (self.gts, self.grs, self.lrs, self.gvs, self.gavs, self.dvs)],
                            None if packed is None else packed.data_ptr())
-        with torch.cuda.device(dev):
+        with _ffi.on_device(dev):
             _ffi.check(self._lib.phc_build_motion_tables(C.byref(bi), C.byref(bo), _ffi.stream_ptr()), "phc_build_motion_tables")
         self.packed = packed
         self.grvs, self.gravs = self.gvs[:, 0], self.gavs[:, 0]            # global_root_(angular_)velocity = body 0 (:408-409)
@@ -232,7 +232,7 @@ class MotionLibBase:
         self._motion_aa = new(int(seg_dst[-1]), aa_w)
         aa = {"src": up(seg_src, torch.int64), "dst": up(seg_dst, torch.int64), "lo": up(c_lo, torch.int64),
               "hi": up(c_lo + kept[seg_slot], torch.int64)}
-        with torch.cuda.device(dev):
+        with _ffi.on_device(dev):
             _ffi.check(self._lib.phc_build_motion_aa(
                 d["pose_aa"].data_ptr(), aa_w, aa["src"].data_ptr(), aa["dst"].data_ptr(), len(seg_len), int(seg_dst[-1]),
                 None if heading is None else meta["heading"].data_ptr(), aa["lo"].data_ptr(), aa["hi"].data_ptr(),
@@ -317,7 +317,7 @@ class MotionLibBase:
             F = int(self.gts.shape[0])
             aux = torch.empty((F, 24, 2), dtype=torch.float32, device=self._device)
             flags = torch.empty(F, dtype=torch.uint8, device=self._device)
-            with torch.cuda.device(self._device):
+            with _ffi.on_device(self._device):
                 _ffi.check(self._lib.phc_build_pair_aux(C.byref(ct), flavour, _ffi.ptr(aux), _ffi.ptr(flags), _ffi.stream_ptr()),
                            "phc_build_pair_aux")
             self._pair[flavour] = (aux, flags)
@@ -337,7 +337,7 @@ class MotionLibBase:
         """Build the B200 frame layout: one contiguous 1248-byte record (gts|grs|gvs|gavs) per frame."""
         F = int(self.gts.shape[0])
         packed = torch.empty((F, 312), dtype=torch.float32, device=self._device)
-        with torch.cuda.device(self._device):
+        with _ffi.on_device(self._device):
             _ffi.check(self._lib.phc_pack_frames(C.byref(self._ctables), _ffi.ptr(packed), _ffi.stream_ptr()), "phc_pack_frames")
         self.packed = packed
         self._ctables = self._make_ctables()
@@ -391,7 +391,7 @@ class MotionLibBase:
             cpu_division = _ffi.ref_device() == _ffi.REF_CPU
         phase, motion_len = phase.contiguous().float(), motion_len.contiguous().float()
         out = torch.empty_like(phase)
-        with torch.cuda.device(self._device):
+        with _ffi.on_device(self._device):
             _ffi.check(self._lib.phc_sample_time_interval(_ffi.ptr(phase), _ffi.ptr(motion_len), phase.numel(),
                                                           0 if cpu_division else 1, _ffi.ptr(out), _ffi.stream_ptr()),
                        "phc_sample_time_interval")
@@ -415,7 +415,7 @@ class MotionLibBase:
                    "blend": torch.empty(B, dtype=torch.float32, device=self._device)}
         so = _ffi.MotionStateOut(*[(out[k].data_ptr() if k in out else None) for k in _ffi.STATE_FIELDS[:13]],
                                  *[(dbg[k].data_ptr() if k in dbg else None) for k in _ffi.STATE_FIELDS[13:]])
-        with torch.cuda.device(self._device):
+        with _ffi.on_device(self._device):
             _ffi.check(self._lib.phc_motion_state(C.byref(self._ctables), _ffi.ptr(ids), _ffi.ptr(times), _ffi.ptr(off), B,
                                                   C.byref(so), _ffi.ref_device(), _ffi.stream_ptr()), "phc_motion_state")
         out.update(dbg)
@@ -435,7 +435,7 @@ class MotionLibBase:
         i0 = torch.empty(n, dtype=torch.int64, device=time.device)
         i1 = torch.empty(n, dtype=torch.int64, device=time.device)
         bl = torch.empty(n, dtype=torch.float32, device=time.device)
-        with torch.cuda.device(time.device):
+        with _ffi.on_device(time.device):
             _ffi.check(self._lib.phc_frame_blend(_ffi.ptr(t), _ffi.ptr(ln), _ffi.ptr(nf), _ffi.ptr(dtt), n, _ffi.ptr(i0), _ffi.ptr(i1),
                                                  _ffi.ptr(bl), _ffi.stream_ptr()), "_calc_frame_blend")
         return i0.view(time.shape), i1.view(time.shape), bl.view(time.shape)
