@@ -221,7 +221,7 @@ def run_reference(args, rank, world):
     print(json.dumps(line), flush=True)
 
 
-def multi_gpu_check(lib, T, N, rank, world, dev, n_check=8192):
+def multi_gpu_check(lib, T, N, rank, world, dev, exchange=None, n_check=8192):
     """Every rank steps its own env shard once (seed 1000 + rank), the moments + episode metrics are all-reduced by
     RunningNorm.finalize (one NCCL message), and then (a) all ranks must hold BIT-IDENTICAL running_mean / running_var / count /
     metric sums and (b) rank 0 repeats the whole thing in one process over the concatenated shards: the result must agree within
@@ -239,6 +239,9 @@ def multi_gpu_check(lib, T, N, rank, world, dev, n_check=8192):
         for r in shards:
             S = synth.make_env_state(T, n_check, seed=1000 + r)
             fs(*[S[k] for k in keys])
+        if allreduce and exchange is not None:
+            exchange.allreduce_finalize(fs, rms)                 # the fused peer-memory kernel
+            return rms, fs.stats[1 + 2 * 934:].clone()
         fs.flush_moments()
         metrics_before = fs.stats[1 + 2 * 934:].clone()
         rms.finalize(allreduce=allreduce)
@@ -249,7 +252,8 @@ def multi_gpu_check(lib, T, N, rank, world, dev, n_check=8192):
     allv = [torch.empty_like(mine) for _ in range(world)]
     dist.all_gather(allv, mine)
     identical = all(bool(torch.equal(allv[0].view(torch.int64), v.view(torch.int64))) for v in allv)
-    res = {"envs_per_rank": n_check, "ranks": world, "ranks_bit_identical": identical}
+    res = {"envs_per_rank": n_check, "ranks": world, "ranks_bit_identical": identical,
+           "exchange": "fused peer-memory kernel (phc_stats_allreduce_finalize)" if exchange is not None else "NCCL all-reduce"}
     if rank == 0:
         one, met1 = run(list(range(world)), False)
         ref = torch.cat([one.running_mean.reshape(-1).double(), one.running_var.reshape(-1).double(), one.count.double(), met1])
@@ -260,7 +264,7 @@ def multi_gpu_check(lib, T, N, rank, world, dev, n_check=8192):
     return res
 
 
-def workload_config(envs, world, sample_note=None):
+def workload_config(envs, world, sample_note=None, exchange_kind=None):
     cfg = {
         "workload": "config4/5: fused rollout-side step (2x motion-state + imitation obs/reward/reset + self obs + RMS norm "
                     "+ moments + GAE amortised), 65536 envs per GPU, 11313-clip AMASS-shaped synthetic library",
@@ -269,6 +273,8 @@ def workload_config(envs, world, sample_note=None):
         "l2": f"{SETS} rotating input/output sets (inputs+outputs {SETS} x ~0.6 GB) > 126 MB L2; library gathers are random over 3.1 GB",
         "rms_update_every": HORIZON,
     }
+    if exchange_kind:
+        cfg["exchange"] = exchange_kind
     if sample_note:
         cfg["sample"] = sample_note
     return cfg
@@ -325,6 +331,10 @@ def main():
     # metrics: the kernel also sums the episode metrics (env-steps, reward, reward_raw[5], resets, terminations) per CTA; they ride in the
     # same statistics buffer as the moments, so rms.finalize() all-reduces both in one message
     fs = FusedStep(lib, N, StepConfig(), rms=rms, normalize=knob_norm, accumulate_moments=knob_mom, defer_moments=True, metrics=True)
+    # the exchange step: one fused kernel over NVLink peer memory (falls back to the NCCL all-reduce inside RunningNorm.finalize
+    # when peer memory cannot be mapped; PHC_BENCH_EXCHANGE=nccl forces that path for A/B runs)
+    from puffer_phc_b200.dist import StatsExchange
+    exchange = None if os.environ.get("PHC_BENCH_EXCHANGE", "p2p") == "nccl" else StatsExchange.create(dev)
     ins, outs = [], []
     for s in range(SETS):
         S = synth.make_env_state(T, N, seed=1 + rank + 100 * s)
@@ -358,9 +368,13 @@ def main():
             compute_gae_cuda(roll["dones"][lo:lo + N], roll["values"][lo:lo + N], roll["rewards"][lo:lo + N], 0.98, 0.2, out=adv[lo:lo + N])
         launches["n"] += 2
         if ((i + 1) % HORIZON == 0 or last) and knob_mom:
-            fs.flush_moments()                         # phc_stats_reduce: folds + clears the per-CTA moment / metric sums of the rollout
-            rms.finalize()                             # ONE all-reduce of [moments | episode metrics] (N>1) + running-average update
-            launches["n"] += 2                         # phc_stats_reduce + phc_rms_finalize (the one memset is torch's)
+            if exchange is not None:
+                exchange.allreduce_finalize(fs)        # ONE kernel: fold the per-CTA sums, all-reduce [moments | metrics] over NVLink peer
+                launches["n"] += 1                     # memory (rank-ordered, bit-identical on all ranks), running-average update
+            else:
+                fs.flush_moments()                     # phc_stats_reduce: folds + clears the per-CTA moment / metric sums of the rollout
+                rms.finalize()                         # ONE NCCL all-reduce of [moments | episode metrics] (N>1) + running-average update
+                launches["n"] += 2                     # phc_stats_reduce + phc_rms_finalize (the one memset is torch's)
         if last:
             stream.wait_stream(gae_stream)             # the timed region ends when both streams have drained
 
@@ -421,7 +435,7 @@ def main():
     # ---- N > 1: numerical self-check of the one exchange step (outside every timed region) --------------------------------------
     check = None
     if world > 1:
-        check = multi_gpu_check(lib, T, N, rank, world, dev)
+        check = multi_gpu_check(lib, T, N, rank, world, dev, exchange)
 
     # ---- the smaller BASELINE configs, reported beside the headline (rank 0, N=1 only; not the bench line) ---------------
     other = None
@@ -526,7 +540,7 @@ def main():
         line = {
             "metric": "env_steps_per_s", "value": value, "unit": "env-steps/s", "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": elapsed_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-            "data": "synthetic", "config": workload_config(N, world),
+            "data": "synthetic", "config": workload_config(N, world, exchange_kind=("fused peer-memory kernel" if exchange is not None else "nccl all-reduce")),
             "roofline": {"bound": "hbm", "kernel": "phc::step_fused_kernel<true>", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": ncu_traffic(N), "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": STEP_BYTES * N,

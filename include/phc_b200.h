@@ -423,6 +423,27 @@ int phc_auto_reset(const phc_motion_tables *t, const phc_reset_env *env, const p
 int phc_stats_reduce(double *moment_partials, int num_partials, int C, int64_t rows, double *row_adjust,
                      double *metric_partials, int num_metric_partials, double *stats, int zero_partials, phc_stream_t stream);
 
+/* The exchange step fused with what precedes and follows it (multi-GPU, one process per GPU, NVLink / NVSwitch peer memory):
+ * phc_stats_reduce + all-reduce(SUM) of [n, sum x, sum x^2 | metrics] over the ranks + phc_rms_finalize as ONE kernel.
+ * Every rank owns an exchange buffer of phc_stats_comm_bytes(world, C) bytes, zero-initialised once, that all ranks can address
+ * (e.g. torch.distributed._symmetric_memory: peer_bufs[r] = the address of rank r's buffer in THIS process; with world == 1 any
+ * device buffer).  Blocks push their folded columns into every rank's buffer with plain stores, publish per-block flags
+ * (st.release.sys) and add the contributions in rank order, so all ranks end with bit-identical running_mean / running_var /
+ * count / metric sums.  epoch: 1, 2, 3, ... the same on every rank, incremented per call (buffers are double-buffered by its
+ * parity).  ticket: a zero-initialised device uint32 owned by the caller.  running_mean / running_var / count may be NULL
+ * (metrics only).  The partial slots and *row_adjust are cleared; stats[1 + 2C ..] += the GLOBAL metric sums. */
+typedef struct phc_stats_comm {
+    int rank, world;               /* world <= 32 */
+    void *peer_bufs[32];           /* [world] device-addressable exchange buffers, index = rank */
+    uint64_t epoch;
+    uint32_t *ticket;
+} phc_stats_comm;
+
+int64_t phc_stats_comm_bytes(int world, int C);
+int phc_stats_allreduce_finalize(double *moment_partials, int num_partials, int C, int64_t rows, double *row_adjust,
+                                 double *metric_partials, int num_metric_partials, double *stats, const phc_stats_comm *comm,
+                                 float *running_mean, float *running_var, float *count, phc_stream_t stream);
+
 /* ------------------------------------------------------------------------------------------- */
 /* RunningNorm (puffer_phc/policies/running_norm.py:5-53)                                       */
 /* ------------------------------------------------------------------------------------------- */

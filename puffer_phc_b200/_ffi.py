@@ -21,7 +21,7 @@ EXPORTS = (
     "phc_imitation_obs_v6", "phc_self_obs_smpl_max", "phc_amp_obs_smpl", "phc_amp_obs_hist_step", "phc_imitation_reward", "phc_im_reset",
     "phc_step_num_partials", "phc_step_fused", "phc_rms_forward", "phc_rms_scratch_doubles", "phc_rms_moments",
     "phc_rms_reduce_partials", "phc_rms_finalize", "phc_auto_reset_num_partials", "phc_auto_reset_scratch_bytes", "phc_auto_reset",
-    "phc_stats_reduce", "phc_gae", "phc_build_motion_tables", "phc_build_motion_aa", "phc_cast_f64_f32", "phc_mpjpe", "phc_frame_blend",
+    "phc_stats_reduce", "phc_stats_comm_bytes", "phc_stats_allreduce_finalize", "phc_gae", "phc_build_motion_tables", "phc_build_motion_aa", "phc_cast_f64_f32", "phc_mpjpe", "phc_frame_blend",
 )
 
 VERSION = 120
@@ -97,6 +97,10 @@ class ResetCfg(C.Structure):
                 ("rms_clip", C.c_float)]
 
 
+class StatsComm(C.Structure):
+    _fields_ = [("rank", C.c_int), ("world", C.c_int), ("peer_bufs", C.c_void_p * 32), ("epoch", C.c_uint64), ("ticket", C.c_void_p)]
+
+
 class BuildIn(C.Structure):
     """phc_build_in (raw clips -> tables, row f4)."""
     _fields_ = [(k, C.c_void_p) for k in ("pose_quat_global", "root_trans", "in_start", "num_frames", "out_start", "fps",
@@ -139,6 +143,8 @@ def _declare(lib):
     lib.phc_auto_reset.argtypes = [C.POINTER(MotionTables), C.POINTER(ResetEnv), C.POINTER(ResetBook), C.POINTER(ResetCfg), P, I64, P, P, P,
                                    P, P, P]
     lib.phc_stats_reduce.argtypes = [P, I, I, I64, P, P, I, P, I, P]
+    lib.phc_stats_comm_bytes.argtypes, lib.phc_stats_comm_bytes.restype = [I, I], I64
+    lib.phc_stats_allreduce_finalize.argtypes = [P, I, I, I64, P, P, I, P, C.POINTER(StatsComm), P, P, P, P]
     lib.phc_build_motion_tables.argtypes = [C.POINTER(BuildIn), C.POINTER(BuildOut), P]
     lib.phc_build_motion_aa.argtypes = [P, I, P, P, I64, I64, P, P, P, P, P]
     lib.phc_cast_f64_f32.argtypes = [P, I64, P, P]

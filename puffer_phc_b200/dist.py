@@ -86,3 +86,67 @@ class EpisodeMetrics:
         b = self.buf.cpu()
         n = max(float(b[0]), 1.0)
         return {k: float(b[i]) / n for i, k in enumerate(self.FIELDS) if i > 0}
+
+
+class StatsExchange:
+    """The hot path's one exchange step as ONE kernel over NVLink peer memory (``phc_stats_allreduce_finalize``, csrc/stats_comm.cu):
+    fold the rank's per-CTA partial sums, all-reduce ``[n, sum x, sum x^2 | episode metrics]`` across the ranks, apply
+    ``RunningNorm``'s running-average update -- instead of ``phc_stats_reduce`` + ``ncclAllReduce`` + ``phc_rms_finalize`` + a memset.
+
+    The exchange buffers are ``torch.distributed._symmetric_memory`` allocations (every rank can address every rank's buffer; the
+    stores travel over NVLink / NVSwitch).  All ranks perform the same fp64 additions in the same order, so running_mean /
+    running_var / count / metric sums are bit-identical across ranks.  With one rank the same kernel runs on a local buffer.
+    ``StatsExchange.create`` returns ``None`` when peer memory cannot be set up (the caller then keeps the NCCL path of
+    ``RunningNorm.finalize``) and says why on stderr."""
+
+    def __init__(self, device, group=None, columns: int = 934):
+        import ctypes as C
+        from . import _ffi
+        self.lib = _ffi.load()
+        self.device = torch.device(device)
+        self.world = dist.get_world_size(group) if (dist.is_available() and dist.is_initialized()) else 1
+        self.rank = dist.get_rank(group) if self.world > 1 else 0
+        self.columns = int(columns)
+        n = int(self.lib.phc_stats_comm_bytes(self.world, self.columns)) // 8 + 1
+        if self.world == 1:
+            self.buf = torch.zeros(n, dtype=torch.float64, device=self.device)
+            ptrs = [self.buf.data_ptr()]
+        else:
+            import torch.distributed._symmetric_memory as symm_mem
+            self.buf = symm_mem.empty(n, dtype=torch.float64, device=self.device)
+            self.buf.zero_()
+            self._hdl = symm_mem.rendezvous(self.buf, group if group is not None else dist.group.WORLD)
+            ptrs = [int(p) for p in self._hdl.buffer_ptrs]
+            torch.cuda.synchronize(self.device)
+            dist.barrier(group)                      # every rank's buffer is zeroed before anyone publishes into it
+        self.ticket = torch.zeros(1, dtype=torch.int32, device=self.device)
+        self.epoch = 0
+        self._comm = _ffi.StatsComm(self.rank, self.world, (C.c_void_p * 32)(*ptrs), 0, self.ticket.data_ptr())
+
+    @classmethod
+    def create(cls, device, group=None, columns: int = 934):
+        try:
+            return cls(device, group, columns)
+        except Exception as exc:       # no NVLink peer mapping (e.g. a PCIe-only box, an old driver): the NCCL all-reduce stays
+            import sys
+            print(f"[puffer_phc_b200] StatsExchange unavailable ({type(exc).__name__}: {exc}); using the NCCL all-reduce", file=sys.stderr)
+            return None
+
+    @torch.no_grad()
+    def allreduce_finalize(self, fused, rms=None) -> None:
+        """``fused.flush_moments()`` + ``rms.finalize()`` in one launch (all ranks must call it the same number of times)."""
+        import ctypes as C
+        from . import _ffi
+        self.epoch += 1
+        self._comm.epoch = self.epoch
+        mp = fused.partials if fused.accumulate_moments else None
+        rows = fused._pending_rows if mp is not None else 0
+        rms = rms if rms is not None else fused.rms
+        upd = rms is not None and mp is not None
+        with _ffi.on_device(self.device):
+            _ffi.check(self.lib.phc_stats_allreduce_finalize(
+                _ffi.ptr(mp), 0 if mp is None else mp.shape[0], self.columns, int(rows), _ffi.ptr(fused.row_adjust) if mp is not None else None,
+                _ffi.ptr(fused.metric_partials), fused.num_partials if fused.metrics else 0, _ffi.ptr(fused.stats), C.byref(self._comm),
+                _ffi.ptr(rms.running_mean) if upd else None, _ffi.ptr(rms.running_var) if upd else None, _ffi.ptr(rms.count) if upd else None,
+                _ffi.stream_ptr()), "phc_stats_allreduce_finalize")
+        fused._pending_rows = 0

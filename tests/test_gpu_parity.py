@@ -534,3 +534,37 @@ def test_pair_tables_do_not_change_the_fused_step(golden, flavour):
         a, b = with_aux[k] + 0.0, without[k] + 0.0         # -0.0 + 0.0 = +0.0
         assert torch.equal(a.view(torch.int32), b.view(torch.int32)), k
     assert torch.equal(with_aux["reset"], without["reset"]) and torch.equal(with_aux["terminated"], without["terminated"])
+
+
+def test_fused_stats_exchange_kernel_equals_reduce_plus_finalize(golden):
+    """phc_stats_allreduce_finalize (fold partials + exchange + running-average update in one kernel; here with one rank) against
+    phc_stats_reduce + phc_rms_finalize: running_mean / running_var / count and the metric sums bit-identical, slots cleared."""
+    from puffer_phc_b200 import synth
+    from puffer_phc_b200.dist import StatsExchange
+    from puffer_phc_b200.fused_step import FusedStep, StepConfig
+    from puffer_phc_b200.motion_lib import MotionLibSMPL
+    from puffer_phc_b200.policies.running_norm import RunningNorm
+    T = synth.make_motion_library(100, seed=2, device=DEV)
+    lib = MotionLibSMPL.from_tables(T, device=DEV)
+    N = 5000
+    S = [synth.make_env_state(T, N, seed=40 + i) for i in range(3)]
+    keys = ("body_state", "progress", "start_time", "start_offset", "motion_ids", "global_offset", "dof_force", "dof_vel")
+    res = []
+    for fused_exchange in (False, True):
+        rms = RunningNorm(934).to(DEV)
+        fs = FusedStep(lib, N, StepConfig(ref_device="cpu"), rms=rms, normalize=True, accumulate_moments=True, defer_moments=True, metrics=True)
+        ex = StatsExchange(DEV) if fused_exchange else None
+        for rollout in range(2):                    # two updates: the second one uses count = 2 and the first one's statistics
+            for s in S:
+                fs(*[s[k] for k in keys])
+            if ex is not None:
+                ex.allreduce_finalize(fs)
+            else:
+                fs.flush_moments()
+                rms.finalize()
+        torch.cuda.synchronize()
+        assert float(fs.partials.abs().sum()) == 0 and float(fs.metric_partials.abs().sum()) == 0 and fs._pending_rows == 0
+        res.append((rms.running_mean.clone(), rms.running_var.clone(), rms.count.clone(), fs.stats[1 + 2 * 934:].clone()))
+    for a, b, what in zip(res[0], res[1], ("running_mean", "running_var", "count", "metric sums")):
+        assert torch.equal(a, b), what
+    assert float(res[1][2]) == 3.0 and float(res[1][3][0]) == 2 * 3 * N
