@@ -410,7 +410,8 @@ def main():
     # ---- e2e: the public API with HOST buffers (H2D inputs + kernel + D2H results inside the timed region) ---------
     e2e = None
     if not args.no_e2e:
-        hin = [{k: v.cpu().pin_memory() for k, v in ins[s].items()} for s in range(2)]
+        from puffer_phc_b200 import hostmem           # the simulator-side buffers: pinned on the NUMA node this rank's GPU hangs off
+        hin = [{k: hostmem.pinned_like(v, dev) for k, v in ins[s].items()} for s in range(2)]
         for i in range(3):
             fs.step_host(hin[i % 2])
         barrier()

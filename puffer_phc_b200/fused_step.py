@@ -227,10 +227,11 @@ class FusedStep:
         keys = [k for k in self._HOST_KEYS if k in host and (self.cfg.use_power_reward or not k.startswith("dof_"))]
         if not hasattr(self, "_dev_in"):
             self._dev_in = {k: torch.empty(host[k].shape, dtype=host[k].dtype, device=self.device) for k in keys}
-            self._host_out = {"reward": torch.empty(self.N, dtype=torch.float32).pin_memory(),
-                              "reward_raw": torch.empty((self.N, self.raw_dim), dtype=torch.float32).pin_memory(),
-                              "reset": torch.empty(self.N, dtype=torch.bool).pin_memory(),
-                              "terminated": torch.empty(self.N, dtype=torch.bool).pin_memory()}
+            from . import hostmem                    # result buffers pinned on the NUMA node this GPU hangs off
+            self._host_out = {"reward": hostmem.pinned_empty(self.N, torch.float32, self.device),
+                              "reward_raw": hostmem.pinned_empty((self.N, self.raw_dim), torch.float32, self.device),
+                              "reset": hostmem.pinned_empty(self.N, torch.bool, self.device),
+                              "terminated": hostmem.pinned_empty(self.N, torch.bool, self.device)}
             self.host_h2d_bytes = sum(host[k].numel() * host[k].element_size() for k in keys)
             self.host_d2h_bytes = sum(v.numel() * v.element_size() for v in self._host_out.values())
         for k in keys:
