@@ -260,8 +260,13 @@ def on_device(dev):
 
 
 def stream_ptr():
+    """The current CUDA stream of the current device as a raw pointer (torch's C accessor: ~0.3 us; building a torch.cuda.Stream
+    object for every call costs ~3.5 us, as much as the launch itself)."""
     import torch
-    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    try:
+        return C.c_void_p(torch._C._cuda_getCurrentRawStream(torch.cuda.current_device()))
+    except AttributeError:
+        return C.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
 def ptr(t):

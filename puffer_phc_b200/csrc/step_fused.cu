@@ -331,8 +331,11 @@ __device__ __forceinline__ void issue_env(const StepArgs& a, const EnvPlan& p, i
     }
 }
 
+// The rotation block of a staged frame starts 288 bytes into a 16-byte aligned record: one 16-byte shared-memory load per lane
+// (four scalar loads at a stride of four floats would put lanes j, j + 8 and j + 16 on the same banks).
 __device__ __forceinline__ BodyState read_frame(const float* f, int j) {
-    return BodyState{ld3(f + 3 * j), ld4(f + 72 + 4 * j), ld3(f + 168 + 3 * j), ld3(f + 240 + 3 * j)};
+    const float4 q = *reinterpret_cast<const float4*>(f + 72 + 4 * j);
+    return BodyState{ld3(f + 3 * j), Q4{q.x, q.y, q.z, q.w}, ld3(f + 168 + 3 * j), ld3(f + 240 + 3 * j)};
 }
 
 __device__ __forceinline__ void store_ref(float* dst, int j, const BodyState& r) {
@@ -413,8 +416,10 @@ __global__ void __maxnreg__(ST_MAXREG) step_fused_kernel(const StepArgs a) {   /
             Q4 root_q{0.0f, 0.0f, 0.0f, 1.0f};
             float power = 0.0f;
             if (valid) {
-                root_p = ld3(wbuf);
-                root_q = ld4(wbuf + 3);
+                if (role == 1) {                 // only the observation role works in the heading frame of the simulated root
+                    root_p = ld3(wbuf);
+                    root_q = ld4(wbuf + 3);
+                }
                 const float* sj = wbuf + REC * j;
                 body = BodyState{ld3(sj), ld4(sj + 3), ld3(sj + 7), ld3(sj + 10)};
                 const BodyState F0 = read_frame(wbuf + FRAME_F, j);
@@ -606,20 +611,20 @@ __global__ void __maxnreg__(ST_MAXREG) step_fused_kernel(const StepArgs a) {   /
         }
         // VEC = contiguous, aligned output rows (the normal case): one float2 store per pair, no pitched-row code in the loop
         // (predicated-off stores would still occupy load/store issue slots).
-        auto column_pass = [&](const float* tile, int64_t e0, int r, auto vec) {
+        // (row pointers are advanced by the caller: no 64-bit index arithmetic per pair in the loop)
+        auto column_pass = [&](const float* trow, float* orow, float* nrow, auto vec) {
             constexpr bool VEC = decltype(vec)::value;
 #pragma unroll
             for (int u = 0; u < ST_WPAIRS; ++u) {
                 const int c = 2 * (wtid + u * ST_WTHREADS);
                 if (c < OBS_W) {
-                    const float2 x = *reinterpret_cast<const float2*>(tile + r * OBS_W + c);
-                    if (!VEC) { float* o = out.obs + (e0 + r) * out.obs_stride + c; o[0] = x.x; o[1] = x.y; }
+                    const float2 x = *reinterpret_cast<const float2*>(trow + c);
+                    if (!VEC) { orow[c] = x.x; orow[c + 1] = x.y; }
                     if (do_norm) {   // (x - mean) / sqrt(var + eps) as a multiplication by the column's reciprocal (<= 1.5 ulp)
                         const float y0 = clamp_nan((x.x - c_mean[u].x) * c_inv[u].x, cfg.rms_clip);
                         const float y1 = clamp_nan((x.y - c_mean[u].y) * c_inv[u].y, cfg.rms_clip);
-                        float* o = out.obs_norm + (e0 + r) * out.obs_stride + c;
-                        if (VEC) *reinterpret_cast<float2*>(o) = make_float2(y0, y1);
-                        else { o[0] = y0; o[1] = y1; }
+                        if (VEC) *reinterpret_cast<float2*>(nrow + c) = make_float2(y0, y1);
+                        else { nrow[c] = y0; nrow[c + 1] = y1; }
                     }
                     if (do_mom) {    // xd*xd is exact in fp64, so fma(xd, xd, q) equals q + xd*xd
                         const double x0 = (double)x.x, x1 = (double)x.y;
@@ -655,12 +660,17 @@ __global__ void __maxnreg__(ST_MAXREG) step_fused_kernel(const StepArgs a) {   /
             // ---- normalised copy + fp64 column moments from the same tile ----------------------------------------
             if (!a.obs_vec || do_norm || do_mom) {
                 // rolled on purpose: three warp roles share the instruction cache, and the pairs give the ILP
+                const float* trow = tile;
                 if (a.obs_vec) {
+                    float* nrow = do_norm ? out.obs_norm + e0 * OBS_W : nullptr;
 #pragma unroll 1
-                    for (int r = 0; r < rows; ++r) column_pass(tile, e0, r, std::true_type{});
+                    for (int r = 0; r < rows; ++r, trow += OBS_W, nrow += OBS_W) column_pass(trow, nullptr, nrow, std::true_type{});
                 } else {
+                    float* orow = out.obs + e0 * out.obs_stride;
+                    float* nrow = do_norm ? out.obs_norm + e0 * out.obs_stride : nullptr;
 #pragma unroll 1
-                    for (int r = 0; r < rows; ++r) column_pass(tile, e0, r, std::false_type{});
+                    for (int r = 0; r < rows; ++r, trow += OBS_W, orow += out.obs_stride, nrow += out.obs_stride)
+                        column_pass(trow, orow, nrow, std::false_type{});
                 }
             }
             if (bulk && wtid == 0) bulk_wait_read();     // the TMA engine has finished reading the tile from shared memory

@@ -176,13 +176,15 @@ def compute_humanoid_im_reset(reset_buf, progress_buf, contact_buf, contact_body
     pos, ref = _prep(rigid_body_pos, ref_body_pos)
     _ffi.require_cuda(progress_buf, pass_time, termination_distance)
     B, J = pos.shape[0], pos.shape[1]
-    prog = progress_buf.to(torch.int16).contiguous()
-    pt = pass_time.to(torch.bool).contiguous()
-    td = termination_distance.to(torch.float32).reshape(-1).contiguous()
+    prog = progress_buf if (progress_buf.dtype == torch.int16 and progress_buf.is_contiguous()) else progress_buf.to(torch.int16).contiguous()
+    pt = pass_time if (pass_time.dtype == torch.bool and pass_time.is_contiguous()) else pass_time.to(torch.bool).contiguous()
+    td = termination_distance
+    if td.dtype != torch.float32 or td.dim() != 1 or not td.is_contiguous():
+        td = td.to(torch.float32).reshape(-1).contiguous()
     if td.numel() == 1 and J > 1:
         td = td.expand(J).contiguous()
-    reset = torch.empty(B, dtype=torch.bool, device=pos.device)
-    term = torch.empty(B, dtype=torch.bool, device=pos.device)
+    flags = torch.empty((2, B), dtype=torch.bool, device=pos.device)     # one allocation for both outputs
+    reset, term = flags[0], flags[1]
     with _ffi.on_device(pos.device):
         _ffi.check(lib.phc_im_reset(_ffi.ptr(prog), _ffi.view3(pos), _ffi.view3(ref), _ffi.ptr(pt), int(bool(enable_early_termination)),
                                     _ffi.ptr(td), int(bool(use_mean)), B, J, _ffi.ptr(reset), _ffi.ptr(term), _ffi.ref_device(),
