@@ -32,7 +32,20 @@ constexpr int AR_THREADS = 256;      // 4 envs per thread
 constexpr int AR_TWARPS = 8;         // warps per tail CTA
 constexpr int AR_MAX_BLOCKS = 4096;  // N <= 4 Mi envs per call
 constexpr int AR_ROW = 936;          // floats per row buffer (934 padded to a multiple of 4)
+constexpr int AR_COLS = (934 + 31) / 32;   // observation columns per lane
 constexpr int AR_NM = 12;            // metric sums the scan kernel forms: PHC_M_REWARD .. PHC_M_EPISODES
+
+// What the tail needs to know about a flagged env, gathered by the (massively parallel) scan kernel so that the tail's per-env chain
+// of dependent loads is: this record -> both frame gathers -> math, instead of id -> motion meta -> offset -> frames -> frames.
+struct __align__(16) ARec {
+    int32_t e_local;     // env = block * AR_BLOCK + e_local
+    int32_t truncated;   // flagged but not terminated
+    int64_t id;          // _sampled_motion_ids[e]
+    int64_t nf, ls;      // _motion_num_frames[id], length_starts[id]
+    float mlen, mdt;     // _motion_lengths[id], _motion_dt[id]
+    float offx, offy, offz, pad;   // _global_offset[e] before it is cleared
+};
+static_assert(sizeof(ARec) == 64, "record layout");
 
 struct ARArgs {
     phc_motion_tables t;
@@ -45,7 +58,7 @@ struct ARArgs {
     int32_t* reset_count;
     int32_t* block_counts;      // [nb]
     double* block_metrics;      // [nb][PHC_NUM_METRICS]
-    int32_t* block_ids;         // [nb][AR_BLOCK] offsets of the block's flagged envs, ascending
+    ARec* block_recs;           // [nb][AR_BLOCK] records of the block's flagged envs, ascending env order
     int nb;
     double* moment_partials;    // [grid][2][934] or NULL
     double* row_adjust;         // [1] or NULL: -= truncated rows
@@ -126,10 +139,24 @@ __global__ void __launch_bounds__(AR_THREADS) auto_reset_scan_kernel(const ARArg
         total += s_cnt[w];
     }
     int pos = woff + incl - cnt;
-    int32_t* ids = a.block_ids + (int64_t)blockIdx.x * AR_BLOCK;
+    ARec* recs = a.block_recs + (int64_t)blockIdx.x * AR_BLOCK;
 #pragma unroll
     for (int k = 0; k < 4; ++k)
-        if ((flagged >> k) & 1u) ids[pos++] = tid * 4 + k;
+        if ((flagged >> k) & 1u) {
+            const int64_t e = e0 + k;
+            const int64_t id = __ldg(env.motion_ids + e);
+            ARec rc;
+            rc.e_local = tid * 4 + k;
+            rc.truncated = env.terminated[e] == 0;
+            rc.id = id;
+            rc.nf = __ldg(a.t.num_frames + id);
+            rc.ls = __ldg(a.t.length_starts + id);
+            rc.mlen = __ldg(a.t.motion_len + id);
+            rc.mdt = __ldg(a.t.motion_dt + id);
+            rc.offx = env.global_offset[e * 3]; rc.offy = env.global_offset[e * 3 + 1]; rc.offz = env.global_offset[e * 3 + 2];
+            rc.pad = 0.0f;
+            recs[pos++] = rc;
+        }
     if (tid == 0) a.block_counts[blockIdx.x] = total;
     if (tid < AR_NM) {
         double s = s_m[0][tid];
@@ -139,17 +166,24 @@ __global__ void __launch_bounds__(AR_THREADS) auto_reset_scan_kernel(const ARArg
     }
 }
 
-// get_motion_state for one body (motion_lib.py:596-610), reference operation order (every lerp two products and a sum)
-__device__ __forceinline__ BodyState query_body(const phc_motion_tables& T, int64_t f0, int64_t f1, float blend, int j, V3 off, int dev) {
+// get_motion_state for one body (motion_lib.py:596-610), reference operation order (every lerp two products and a sum), split into
+// the gathers and the math so that the gathers of BOTH queries of a reset are in flight together.
+struct RawPair { V3 p0, p1, v0, v1, w0, w1; Q4 q0, q1; };
+__device__ __forceinline__ RawPair load_pair(const phc_motion_tables& T, int64_t f0, int64_t f1, int j) {
+    RawPair r;
+    r.p0 = ldg3(T.gts + (f0 * NB + j) * 3); r.p1 = ldg3(T.gts + (f1 * NB + j) * 3);
+    r.v0 = ldg3(T.gvs + (f0 * NB + j) * 3); r.v1 = ldg3(T.gvs + (f1 * NB + j) * 3);
+    r.w0 = ldg3(T.gavs + (f0 * NB + j) * 3); r.w1 = ldg3(T.gavs + (f1 * NB + j) * 3);
+    r.q0 = ldg4a(T.grs + (f0 * NB + j) * 4); r.q1 = ldg4a(T.grs + (f1 * NB + j) * 4);
+    return r;
+}
+__device__ __forceinline__ BodyState blend_pair(const RawPair& a, float blend, V3 off, int dev) {
     const float om = 1.0f - blend;
-    const V3 p0 = ldg3(T.gts + (f0 * NB + j) * 3), p1 = ldg3(T.gts + (f1 * NB + j) * 3);
-    const V3 v0 = ldg3(T.gvs + (f0 * NB + j) * 3), v1 = ldg3(T.gvs + (f1 * NB + j) * 3);
-    const V3 w0 = ldg3(T.gavs + (f0 * NB + j) * 3), w1 = ldg3(T.gavs + (f1 * NB + j) * 3);
     BodyState r;
-    r.p = V3{lerp(p0.x, p1.x, om, blend) + off.x, lerp(p0.y, p1.y, om, blend) + off.y, lerp(p0.z, p1.z, om, blend) + off.z};
-    r.q = slerp_rcp(ldg4a(T.grs + (f0 * NB + j) * 4), ldg4a(T.grs + (f1 * NB + j) * 4), blend, dev);
-    r.v = V3{lerp(v0.x, v1.x, om, blend), lerp(v0.y, v1.y, om, blend), lerp(v0.z, v1.z, om, blend)};
-    r.w = V3{lerp(w0.x, w1.x, om, blend), lerp(w0.y, w1.y, om, blend), lerp(w0.z, w1.z, om, blend)};
+    r.p = V3{lerp(a.p0.x, a.p1.x, om, blend) + off.x, lerp(a.p0.y, a.p1.y, om, blend) + off.y, lerp(a.p0.z, a.p1.z, om, blend) + off.z};
+    r.q = slerp_rcp(a.q0, a.q1, blend, dev);
+    r.v = V3{lerp(a.v0.x, a.v1.x, om, blend), lerp(a.v0.y, a.v1.y, om, blend), lerp(a.v0.z, a.v1.z, om, blend)};
+    r.w = V3{lerp(a.w0.x, a.w1.x, om, blend), lerp(a.w0.y, a.w1.y, om, blend), lerp(a.w0.z, a.w1.z, om, blend)};
     return r;
 }
 
@@ -158,7 +192,9 @@ __global__ void __launch_bounds__(AR_TWARPS * 32) auto_reset_tail_kernel(const A
     const bool mom = a.moment_partials != nullptr;
     double* acc = smem_d;                                                        // [AR_TWARPS][2][OBS_W] (only with moments)
     float* rows = reinterpret_cast<float*>(smem_d + (mom ? AR_TWARPS * 2 * OBS_W : 0));   // [AR_TWARPS][AR_ROW]
-    int* prefix = reinterpret_cast<int*>(rows + AR_TWARPS * AR_ROW);             // [nb + 1] exclusive prefix of the block counts
+    float* s_mean = rows + AR_TWARPS * AR_ROW;                                   // [AR_ROW] RunningNorm mean (only with obs_norm)
+    float* s_inv = s_mean + AR_ROW;                                              // [AR_ROW] 1 / sqrt(var + eps), one IEEE sqrt + division per column per CTA
+    int* prefix = reinterpret_cast<int*>(s_inv + AR_ROW);                        // [nb + 1] exclusive prefix of the block counts
     __shared__ int s_part[AR_TWARPS * 32];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const phc_motion_tables& T = a.t;
@@ -175,6 +211,11 @@ __global__ void __launch_bounds__(AR_TWARPS * 32) auto_reset_tail_kernel(const A
     s_part[tid] = local;
     if (mom)
         for (int i = tid; i < AR_TWARPS * 2 * OBS_W; i += AR_TWARPS * 32) acc[i] = 0.0;
+    if (env.obs_norm)
+        for (int c = tid; c < OBS_W; c += AR_TWARPS * 32) {
+            s_mean[c] = __ldg(env.rms_mean + c);
+            s_inv[c] = 1.0f / sqrtf(__ldg(env.rms_var + c) + cfg.rms_eps);
+        }
     __syncthreads();
     if (tid == 0) {
         int run = 0;
@@ -215,12 +256,22 @@ __global__ void __launch_bounds__(AR_TWARPS * 32) auto_reset_tail_kernel(const A
             const int mid = (lo + hi) >> 1;
             if (prefix[mid] <= r) lo = mid; else hi = mid;
         }
-        const int64_t e = (int64_t)lo * AR_BLOCK + a.block_ids[(int64_t)lo * AR_BLOCK + (r - prefix[lo])];
+        const ARec rc = a.block_recs[(int64_t)lo * AR_BLOCK + (r - prefix[lo])];     // one 64-byte record, the same for every lane
+        const int64_t e = (int64_t)lo * AR_BLOCK + rc.e_local;
         if (lane == 0 && a.reset_ids) a.reset_ids[r] = e;        // ascending env order = torch.nonzero order
-        const bool truncated = env.terminated[e] == 0;          // flagged and not terminated (read before the flags are cleared)
-        const int64_t id = __ldg(env.motion_ids + e);
-        const float mlen = __ldg(T.motion_len + id), mdt = __ldg(T.motion_dt + id);
-        const int64_t nf = __ldg(T.num_frames + id), ls = __ldg(T.length_starts + id);
+        const bool truncated = rc.truncated != 0;               // flagged and not terminated
+        float* orow = env.obs + e * env.obs_stride;
+        float* nrow = env.obs_norm ? env.obs_norm + e * env.obs_stride : nullptr;
+        // the pre-reset observation row (only needed for the moment correction): all 30 loads per lane are issued here, before the two
+        // motion-state queries, so that their latency hides behind the gathers and the math instead of following them
+        float ov[AR_COLS];
+#pragma unroll
+        for (int k = 0; k < AR_COLS; ++k) {
+            const int c = lane + 32 * k;
+            ov[k] = (mom && c < OBS_W) ? orow[c] : 0.0f;
+        }
+        const float mlen = rc.mlen, mdt = rc.mdt;
+        const int64_t nf = rc.nf, ls = rc.ls;
         // _sample_ref_state (:843-857): StateInit.Random / Hybrid sample a frame-quantised start time, Start and flag_test use 0
         float start = 0.0f;
         if (cfg.state_init == 0 && !cfg.flag_test) {
@@ -228,14 +279,28 @@ __global__ void __launch_bounds__(AR_TWARPS * 32) auto_reset_tail_kernel(const A
             const float qv = cfg.ref_device == PHC_REF_CUDA ? x * (float)(1.0 / (1.0 / 30.0)) : x / fps;
             start = (float)(int64_t)qv * fps;
         }
-        __syncwarp();
-        const V3 off_old = ld3(env.global_offset + e * 3);       // the query uses the env's CURRENT offset (:859-861) ...
-        int64_t i0, i1;
-        float bl;
+        const V3 off_old{rc.offx, rc.offy, rc.offz};             // the query uses the env's CURRENT offset (:859-861) ...
+        // both queries of the reset -- the new state at `start`, the reference of the observation at t+1 = (0 + 1) * dt + start + 0
+        // (:935-959, offset now zero) -- depend on the record only: their gathers are issued back to back
+        int64_t i0, i1, k0, k1;
+        float bl, bl1;
         frame_blend(start, mlen, nf, mdt, i0, i1, bl);
+        const float t1 = ((float)(int16_t)1 * cfg.dt + start) + 0.0f;
+        frame_blend(t1, mlen, nf, mdt, k0, k1, bl1);
         const int j = lane;
+        RawPair ra{}, rb{};
+        Q4 l0{}, l1{};
+        V3 d0{}, d1{};
+        if (j < NB) {
+            ra = load_pair(T, i0 + ls, i1 + ls, j);
+            rb = load_pair(T, k0 + ls, k1 + ls, j);
+            if (j >= 1) {
+                if (env.dof_pos) { l0 = ldg4a(T.lrs + ((i0 + ls) * NB + j) * 4); l1 = ldg4a(T.lrs + ((i1 + ls) * NB + j) * 4); }
+                if (env.dof_vel) { d0 = ldg3(T.dvs + ((i0 + ls) * 23 + (j - 1)) * 3); d1 = ldg3(T.dvs + ((i1 + ls) * 23 + (j - 1)) * 3); }
+            }
+        }
         BodyState b{};
-        if (j < NB) b = query_body(T, i0 + ls, i1 + ls, bl, j, off_old, cfg.ref_device);
+        if (j < NB) b = blend_pair(ra, bl, off_old, cfg.ref_device);
         // ---- _set_env_state (:899-929) ----------------------------------------------------------------------------------
         if (j < NB) {
             float* o = env.body_state + e * env.env_stride + REC * j;
@@ -245,19 +310,13 @@ __global__ void __launch_bounds__(AR_TWARPS * 32) auto_reset_tail_kernel(const A
                 st3(rs, b.p); st4(rs + 3, b.q); st3(rs + 7, b.v); st3(rs + 10, b.w);
             }
             if (j >= 1) {
-                const int64_t f0 = i0 + ls, f1 = i1 + ls;
-                if (env.dof_pos) {
-                    const Q4 lr = slerp_rcp(ldg4a(T.lrs + (f0 * NB + j) * 4), ldg4a(T.lrs + (f1 * NB + j) * 4), bl, cfg.ref_device);
-                    st3(env.dof_pos + e * NDOF + (j - 1) * 3, quat_exp_map_fast(lr));
-                }
+                if (env.dof_pos) st3(env.dof_pos + e * NDOF + (j - 1) * 3, quat_exp_map_fast(slerp_rcp(l0, l1, bl, cfg.ref_device)));
                 if (env.dof_vel) {
                     const float om = 1.0f - bl;
-                    const V3 d0 = ldg3(T.dvs + (f0 * 23 + (j - 1)) * 3), d1 = ldg3(T.dvs + (f1 * 23 + (j - 1)) * 3);
                     st3(env.dof_vel + e * NDOF + (j - 1) * 3, V3{lerp(d0.x, d1.x, om, bl), lerp(d0.y, d1.y, om, bl), lerp(d0.z, d1.z, om, bl)});
                 }
             }
         }
-        __syncwarp();                                            // every lane has read the old offset before lane 0 clears it
         if (lane == 0) {                                         // :721-727, :774-777
             env.global_offset[e * 3] = 0.0f; env.global_offset[e * 3 + 1] = 0.0f; env.global_offset[e * 3 + 2] = 0.0f;
             env.start_time[e] = start;
@@ -266,11 +325,9 @@ __global__ void __launch_bounds__(AR_TWARPS * 32) auto_reset_tail_kernel(const A
             env.reset[e] = 0;
             env.terminated[e] = 0;
         }
-        // ---- _compute_observations(env_ids) (:935-959): reference at t+1 = (0 + 1) * dt + start + 0, offset now zero -------------
-        const float t1 = ((float)(int16_t)1 * cfg.dt + start) + 0.0f;
-        frame_blend(t1, mlen, nf, mdt, i0, i1, bl);
+        // ---- _compute_observations(env_ids) (:935-959) against the reference at t+1 -------------------------------------------------
         BodyState ref{};
-        if (j < NB) ref = query_body(T, i0 + ls, i1 + ls, bl, j, V3{0.0f, 0.0f, 0.0f}, cfg.ref_device);
+        if (j < NB) ref = blend_pair(rb, bl1, V3{0.0f, 0.0f, 0.0f}, cfg.ref_device);
         const V3 root_p{__shfl_sync(FULL, b.p.x, 0), __shfl_sync(FULL, b.p.y, 0), __shfl_sync(FULL, b.p.z, 0)};
         const Q4 root_q{__shfl_sync(FULL, b.q.x, 0), __shfl_sync(FULL, b.q.y, 0), __shfl_sync(FULL, b.q.z, 0), __shfl_sync(FULL, b.q.w, 0)};
         float hz, hw;
@@ -283,21 +340,22 @@ __global__ void __launch_bounds__(AR_TWARPS * 32) auto_reset_tail_kernel(const A
                           q + 432 + 6 * j);
         }
         __syncwarp();
-        float* orow = env.obs + e * env.obs_stride;
-        float* nrow = env.obs_norm ? env.obs_norm + e * env.obs_stride : nullptr;
-        for (int c = lane; c < OBS_W; c += 32) {
-            const float nv = row[c];
-            if (mom) {
-                const double od = (double)orow[c], nd = (double)nv;
-                if (truncated) { wacc[c] -= od; wacc[OBS_W + c] -= od * od; }
-                else { wacc[c] += nd - od; wacc[OBS_W + c] += nd * nd - od * od; }
-            }
-            orow[c] = nv;
-            if (nrow) {
-                const float inv = 1.0f / sqrtf(__ldg(env.rms_var + c) + cfg.rms_eps);
-                float y = (nv - __ldg(env.rms_mean + c)) * inv;
-                y = (y != y) ? y : fminf(fmaxf(y, -cfg.rms_clip), cfg.rms_clip);
-                nrow[c] = y;
+#pragma unroll
+        for (int k = 0; k < AR_COLS; ++k) {
+            const int c = lane + 32 * k;
+            if (c < OBS_W) {
+                const float nv = row[c];
+                if (mom) {
+                    const double od = (double)ov[k], nd = (double)nv;
+                    if (truncated) { wacc[c] -= od; wacc[OBS_W + c] -= od * od; }
+                    else { wacc[c] += nd - od; wacc[OBS_W + c] += nd * nd - od * od; }
+                }
+                orow[c] = nv;
+                if (nrow) {
+                    float y = (nv - s_mean[c]) * s_inv[c];
+                    y = (y != y) ? y : fminf(fmaxf(y, -cfg.rms_clip), cfg.rms_clip);
+                    nrow[c] = y;
+                }
             }
         }
         __syncwarp();
@@ -370,7 +428,7 @@ extern "C" int phc_auto_reset_num_partials(void) { return sm_count(); }
 extern "C" int64_t phc_auto_reset_scratch_bytes(int64_t N) {
     if (N <= 0) return 0;
     const int64_t nb = ar_blocks(N);
-    return nb * (int64_t)(sizeof(int32_t) + PHC_NUM_METRICS * sizeof(double) + AR_BLOCK * sizeof(int32_t)) + 64;
+    return nb * (int64_t)(sizeof(int32_t) + PHC_NUM_METRICS * sizeof(double) + AR_BLOCK * sizeof(ARec)) + 128;
 }
 
 extern "C" int phc_auto_reset(const phc_motion_tables* t, const phc_reset_env* env, const phc_reset_book* book,
@@ -381,7 +439,7 @@ extern "C" int phc_auto_reset(const phc_motion_tables* t, const phc_reset_env* e
     PHC_REQUIRE(N >= 0, PHC_EINVAL, "%s: N < 0", fn);
     if (N == 0) return PHC_OK;
     PHC_REQUIRE(ar_blocks(N) <= AR_MAX_BLOCKS, PHC_EUNSUPPORTED, "%s: N=%lld > %d envs per call", fn, (long long)N, AR_MAX_BLOCKS * AR_BLOCK);
-    PHC_REQUIRE(scratch && aligned8(scratch), PHC_EINVAL, "%s: scratch is NULL or not 8-byte aligned (phc_auto_reset_scratch_bytes)", fn);
+    PHC_REQUIRE(scratch && aligned16(scratch), PHC_EINVAL, "%s: scratch is NULL or not 16-byte aligned (phc_auto_reset_scratch_bytes)", fn);
     PHC_REQUIRE(env->body_state && env->progress && env->start_time && env->start_offset && env->global_offset && env->motion_ids &&
                     env->reset && env->terminated && env->obs, PHC_EINVAL, "%s: a required env tensor is NULL", fn);
     PHC_REQUIRE(env->env_stride >= SIM_F && env->obs_stride >= OBS_W, PHC_ESHAPE, "%s: env_stride / obs_stride too small", fn);
@@ -398,14 +456,14 @@ extern "C" int phc_auto_reset(const phc_motion_tables* t, const phc_reset_env* e
     const int nb = ar_blocks(N);
     char* sp = static_cast<char*>(scratch);
     ARArgs a{*t, *env, *book, *cfg, phase, N, reset_ids, reset_count, nullptr, nullptr, nullptr, nb, moment_partials, row_adjust};
-    a.block_metrics = reinterpret_cast<double*>(sp);
-    a.block_counts = reinterpret_cast<int32_t*>(sp + (size_t)nb * PHC_NUM_METRICS * sizeof(double));
-    a.block_ids = a.block_counts + ((nb + 1) & ~1);
+    a.block_recs = reinterpret_cast<ARec*>(sp);
+    a.block_metrics = reinterpret_cast<double*>(sp + (size_t)nb * AR_BLOCK * sizeof(ARec));
+    a.block_counts = reinterpret_cast<int32_t*>(a.block_metrics + (size_t)nb * PHC_NUM_METRICS);
     cudaStream_t s = (cudaStream_t)stream;
     auto_reset_scan_kernel<<<nb, AR_THREADS, 0, s>>>(a);
     int rc = check_launch(fn);
     if (rc) return rc;
-    const size_t smem = (moment_partials ? (size_t)AR_TWARPS * 2 * OBS_W * sizeof(double) : 0) + (size_t)AR_TWARPS * AR_ROW * sizeof(float) +
+    const size_t smem = (moment_partials ? (size_t)AR_TWARPS * 2 * OBS_W * sizeof(double) : 0) + (size_t)(AR_TWARPS + 2) * AR_ROW * sizeof(float) +
                         (size_t)(nb + 1) * sizeof(int);
     cudaError_t e = cudaFuncSetAttribute(auto_reset_tail_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return fail((int)e, "%s: cudaFuncSetAttribute(%zu B smem): %s", fn, smem, cudaGetErrorString(e));
