@@ -96,7 +96,7 @@ def measured_peak_gbs():
 
 def ncu_traffic(n_envs):
     """DRAM bytes per launch of the dominant kernel from the committed ncu capture (only valid at the captured size)."""
-    p = os.path.join(ROOT, "profiles", "r1_step_fused_traffic.json")
+    p = os.path.join(ROOT, "profiles", "r2_step_fused_traffic.json")
     try:
         t = json.load(open(p))
         if int(t["envs"]) == int(n_envs):

@@ -386,12 +386,20 @@ __global__ void __launch_bounds__(256) stats_reduce_kernel(double* __restrict__ 
     if ((int)blockIdx.x < nblk_cols) {
         const int i = blockIdx.x * 32 + lane;
         double s = 0.0;
-        if (i < ncol && partial)
-            for (int p = g; p < P; p += 8) {
+        if (i < ncol && partial) {              // four independent loads in flight per thread, then their clears (fixed order)
+            int p = g;
+            for (; p + 24 < P; p += 32) {
+                double* q = partial + (int64_t)p * ncol + i;
+                const double x0 = q[0], x1 = q[(int64_t)8 * ncol], x2 = q[(int64_t)16 * ncol], x3 = q[(int64_t)24 * ncol];
+                if (zero) { q[0] = 0.0; q[(int64_t)8 * ncol] = 0.0; q[(int64_t)16 * ncol] = 0.0; q[(int64_t)24 * ncol] = 0.0; }
+                s += (x0 + x1) + (x2 + x3);
+            }
+            for (; p < P; p += 8) {
                 double* q = partial + (int64_t)p * ncol + i;
                 s += *q;
                 if (zero) *q = 0.0;
             }
+        }
         sh[g][lane] = s;
         __syncthreads();
         if (g == 0 && i < ncol) {

@@ -59,12 +59,21 @@ __global__ void __launch_bounds__(256) stats_allreduce_finalize_kernel(const SCA
     if (!metrics_block) {
         const int c = b * SC_COLS + (lane & 15);
         const int i = (lane < 16) ? c : C + c;                     // index into a partial slot: [sum x (C) | sum x^2 (C)]
-        if (c < C && a.partial)
-            for (int p = g; p < a.P; p += 8) {
-                double* q = a.partial + (size_t)p * 2 * C + i;
+        if (c < C && a.partial) {               // four independent loads in flight per thread, then their clears (fixed order)
+            const size_t ps = (size_t)2 * C;
+            int p = g;
+            for (; p + 24 < a.P; p += 32) {
+                double* q = a.partial + (size_t)p * ps + i;
+                const double x0 = q[0], x1 = q[8 * ps], x2 = q[16 * ps], x3 = q[24 * ps];
+                q[0] = 0.0; q[8 * ps] = 0.0; q[16 * ps] = 0.0; q[24 * ps] = 0.0;
+                s += (x0 + x1) + (x2 + x3);
+            }
+            for (; p < a.P; p += 8) {
+                double* q = a.partial + (size_t)p * ps + i;
                 s += *q;
                 *q = 0.0;
             }
+        }
     } else if (a.mpartial && lane < PHC_NUM_METRICS && g == 0) {
         for (int p = 0; p < a.MP; ++p) {
             double* q = a.mpartial + (size_t)p * PHC_NUM_METRICS + lane;

@@ -145,7 +145,7 @@ class StatsExchange:
         upd = rms is not None and mp is not None
         with _ffi.on_device(self.device):
             _ffi.check(self.lib.phc_stats_allreduce_finalize(
-                _ffi.ptr(mp), 0 if mp is None else mp.shape[0], self.columns, int(rows), _ffi.ptr(fused.row_adjust) if mp is not None else None,
+                _ffi.ptr(mp), 0 if mp is None else fused.active_partials(), self.columns, int(rows), _ffi.ptr(fused.row_adjust) if mp is not None else None,
                 _ffi.ptr(fused.metric_partials), fused.num_partials if fused.metrics else 0, _ffi.ptr(fused.stats), C.byref(self._comm),
                 _ffi.ptr(rms.running_mean) if upd else None, _ffi.ptr(rms.running_var) if upd else None, _ffi.ptr(rms.count) if upd else None,
                 _ffi.stream_ptr()), "phc_stats_allreduce_finalize")

@@ -155,6 +155,8 @@ class AutoReset:
         self.fused = fused
         if fused is not None and fused.accumulate_moments and not fused.defer_moments:
             raise ValueError("AutoReset: moment correction needs FusedStep(defer_moments=True)")
+        if fused is not None and fused.accumulate_moments:
+            fused.tail_slots_used = True
         self.metrics = fused.stats[1 + 2 * 934:] if fused is not None else torch.zeros(_ffi.NUM_METRICS, dtype=torch.float64, device=dev)
         self.step_metrics = bool(step_metrics) and not (fused is not None and fused.metrics)
         self._scratch = torch.empty(int(self.lib.phc_auto_reset_scratch_bytes(N)) // 8 + 1, dtype=torch.float64, device=dev)

@@ -95,6 +95,7 @@ class FusedStep:
         self.metrics = bool(metrics)
         self.metric_partials = torch.zeros((self.num_partials, _ffi.NUM_METRICS), dtype=torch.float64, device=dev) if metrics else None
         self.row_adjust = torch.zeros(1, dtype=torch.float64, device=dev)
+        self.tail_slots_used = False     # set by envs.reset.AutoReset: the tail's correction slots then take part in the folds
         # the rank's statistics buffer: [n, sum x, sum x^2 | episode metrics] -- moments and metrics travel in one all-reduce
         self.stats = torch.zeros(1 + 2 * OBS_DIM + _ffi.NUM_METRICS, dtype=torch.float64, device=dev)
         if rms is not None and (accumulate_moments or metrics):
@@ -192,10 +193,14 @@ class FusedStep:
     def _reduce(self, rows: int, zero: bool) -> None:
         """phc_stats_reduce: per-CTA moment / metric partials (+ the auto-reset tail's corrections) -> ``self.stats``."""
         mp = self.partials if self.accumulate_moments else None
-        _ffi.check(self.lib.phc_stats_reduce(_ffi.ptr(mp), 0 if mp is None else (mp.shape[0] if self.defer_moments else self.num_partials),
+        _ffi.check(self.lib.phc_stats_reduce(_ffi.ptr(mp), 0 if mp is None else self.active_partials(),
                                              OBS_DIM, int(rows) if mp is not None else 0, _ffi.ptr(self.row_adjust) if mp is not None else None,
                                              _ffi.ptr(self.metric_partials), self.num_partials if self.metrics else 0,
                                              _ffi.ptr(self.stats), 1 if zero else 0, _ffi.stream_ptr()), "phc_stats_reduce")
+
+    def active_partials(self) -> int:
+        """Partial slots a fold has to visit: the step kernel's, plus the auto-reset tail's once an AutoReset is attached."""
+        return self.partials.shape[0] if (self.defer_moments and self.tail_slots_used) else self.num_partials
 
     def flush_moments(self) -> None:
         """``defer_moments`` mode: fold the sums the kernel has accumulated since the last flush (moments, the auto-reset tail's
