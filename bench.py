@@ -513,7 +513,7 @@ def main():
             name = "config2_4096_envs_fused_step" if n2 == 4096 else f"fused_step_{n2}_envs"
             other[name] = {
                 "us_per_step": us, "env_steps_per_s": n2 / (us * 1e-6), "gbs": gbs2, "frac": gbs2 / peak0,
-                "blocks_per_sm": (n2 / 8) / 148.0,
+                "blocks_per_sm": (n2 / 12) / 148.0,
                 "note": "phc_step_fused replayed from a CUDA graph: launch + pipeline fill (planner -> gathers -> compute -> writers) + "
                         "ceil(blocks per SM) iterations of ~2.6 us; 4096 envs move 59 MB (9 us at the HBM peak), the kernel issues "
                         "~1300 warp-instructions per env (11 us at the measured issue rate)"}

@@ -24,8 +24,9 @@
 //     scalars (coalesced across envs), does the id -> motion-meta lookups and the frame-index / blend arithmetic
 //     (bit-exact op order) and leaves a 48-byte plan per (env, role) in shared memory, so compute warps never
 //     execute (32x redundantly) or wait on that dependent load chain.
-//   * Register budget: each SM sub-partition holds 16384 registers = 5 warps x 96 or 6 warps x 80 (default S = 8: 12 compute + 4 writer
-//     + 1 planner warps).  The flag-critical chain keeps the reference's fp32 op order.
+//   * Register budget: each SM sub-partition holds 16384 registers = 5 warps x 96 or 6 warps x 80.  Default S = 12: 18 compute + 5 writer
+//     + 1 planner warps = 24 warps at 80 registers (no spills in the production instantiation).  The flag-critical chain keeps the
+//     reference's fp32 op order.
 #include <type_traits>
 
 #include "phc_body.cuh"
@@ -33,8 +34,10 @@
 namespace phc {
 
 #ifndef ST_SLOTS
-#define ST_SLOTS 8                                   // envs per CTA iteration (multiple of 4: one compute group = 4 envs)
-#endif
+#define ST_SLOTS 12                                  // envs per CTA iteration (multiple of 4: one compute group = 4 envs).  Round 2: 12 envs
+#endif                                               // (18 compute + 5 writer + 1 planner warps at 80 registers, 0 spills, 214 KB smem)
+                                                     // beat 8 envs (17 warps at 96 registers) by 5.4 % once the pair tables had
+                                                     // trimmed the compute warps: 0.1574 vs 0.1663 ms at 65536 envs
 constexpr int ST_ENVS = ST_SLOTS;
 constexpr int ST_GROUPS = ST_ENVS / 4;               // compute groups per role
 constexpr int ST_CWARPS = 2 * 3 * ST_GROUPS;         // compute warps: 3 warps per group, 2 roles
@@ -53,8 +56,8 @@ static_assert(ST_ENVS % 4 == 0 && ST_NBUF <= 32, "a compute group handles 4 envs
 #define ST_WUNROLL 1
 #endif
 #ifndef ST_WRITERS
-#define ST_WRITERS 4
-#endif
+#define ST_WRITERS 5                                 // 12 slots: 4 writers 0.1594 ms, 5 writers 0.1574 ms; 6 do not fit (25 warps x 80 registers:
+#endif                                               // a seventh warp on one SM sub-partition exceeds its 16384 registers)
 #ifndef ST_TMA_LOADS
 #define ST_TMA_LOADS 0                               // 1: sim record + packed frames arrive by TMA bulk loads (one lane issues three
                                                      // cp.async.bulk with mbarrier byte counting instead of 12 cp.async per lane);
