@@ -23,10 +23,11 @@ buf = np.zeros(160 * 32 * 5, dtype=np.uint64)
 so = _ffi.load()
 so.phc_debug_profile.argtypes = [C.c_void_p]
 assert so.phc_debug_profile(buf.ctypes.data) == 0
-p = buf.reshape(160, 32, 5)[:148, :12].astype(np.float64)
+cw = int(os.environ.get("ST_CWARPS", "18"))          # compute warps: 6 per 4 env slots (default 12 slots)
+p = buf.reshape(160, 32, 5)[:148, :cw].astype(np.float64)
 names = ["landing+group", "plan", "tile_release", "group_barriers", "loop"]
 out = {}
-for role, sl in (("roleA", slice(0, 6)), ("roleB", slice(6, 12))):
+for role, sl in (("roleA", slice(0, cw // 2)), ("roleB", slice(cw // 2, cw))):
     q = p[:, sl]
     out[role] = {n: round(float(q[..., k].sum() / q[..., 4].sum()), 4) for k, n in enumerate(names[:4])}
     out[role]["loop_cycles_mean"] = float(q[..., 4].mean())

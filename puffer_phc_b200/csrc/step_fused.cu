@@ -49,6 +49,9 @@ static_assert(ST_ENVS % 4 == 0 && ST_NBUF <= 32, "a compute group handles 4 envs
 #ifndef ST_WHINT
 #define ST_WHINT 400
 #endif
+#ifndef ST_BHINT
+#define ST_BHINT ST_CHINT                            // suspend-time hint of role B's waits (it idles behind role A through the plan ring)
+#endif
 #ifndef ST_TILES
 #define ST_TILES 2                                   // observation tiles in flight between compute and writer warps
 #endif
@@ -459,7 +462,8 @@ __global__ void __maxnreg__(ST_MAXREG) step_fused_kernel(const StepArgs a) {   /
                 if (nblk < a.num_blocks) {
                     const int d = (it + 1) % ST_PLANS;
                     PROF_BEGIN
-                    mbar_wait<ST_CHINT>(&pfull[d], ((it + 1) / ST_PLANS) & 1);
+                    if (role == 1) mbar_wait<ST_BHINT>(&pfull[d], ((it + 1) / ST_PLANS) & 1);
+                    else mbar_wait<ST_CHINT>(&pfull[d], ((it + 1) / ST_PLANS) & 1);
                     PROF_END(1)
                     nxt = plans[d * ST_NBUF + buf];
                     if (nxt.valid & 1) issue_env<PACKED>(a, nxt, nblk * ST_ENVS + slot, role, wbuf, j, &lfull[buf]);
@@ -472,7 +476,7 @@ __global__ void __maxnreg__(ST_MAXREG) step_fused_kernel(const StepArgs a) {   /
             // ST_TILES = 2 its six arrivals of iteration it could otherwise pair up with its own six of iteration it - 2 while role B
             // is still writing that older tile (the plan wait below holds role A back everywhere except in a CTA's last
             // iteration, which has no next plan).  The wait is one try_wait that succeeds at once whenever role A is the slower role.
-            if ((ST_A_WAITS_TILE || role == 1) && use >= 1) mbar_wait<ST_CHINT>(&empty[b], (use - 1) & 1);
+            if ((ST_A_WAITS_TILE || role == 1) && use >= 1) mbar_wait<ST_BHINT>(&empty[b], (use - 1) & 1);
             else if (ST_SPLIT_DONE) { if (it >= ST_META) mbar_wait<ST_CHINT>(&adone[it & (ST_META - 1)], ((it / ST_META) - 1) & 1); }
             else if (!ST_DIAG_NOFULLWAIT && use >= 1) mbar_wait<ST_CHINT>(&full[b], (use - 1) & 1);
             PROF_END(2)
