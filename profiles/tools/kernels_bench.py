@@ -2,6 +2,8 @@
 achieved GB/s on the algorithmic bytes of DESIGN.md section 4 against the measured HBM peak.
 
     python profiles/tools/kernels_bench.py > gpurun_out/kernels.json
+    KB_ONCE=1 ncu --set full -k regex:"reward_kernel|gae_" -c 8 python profiles/tools/kernels_bench.py      (two calls per entry point
+                                                                                                          at 65536 envs, nothing timed)
 """
 import json
 import os
@@ -97,6 +99,12 @@ def main():
             ("RunningNorm.update [N,934]", 3736, [lambda i=i: rn.update(obs[i]) for i in range(4)]),
             ("c_gae.compute_gae [N*32]", 16 * 32, [lambda i=i: compute_gae_cuda(roll[i]["dones"], roll[i]["values"], roll[i]["rewards"], 0.98, 0.2) for i in range(2)]),
         ]
+        if os.environ.get("KB_ONCE"):
+            for name, _, fns in cases:
+                fns[0]()
+                fns[1]()
+            torch.cuda.synchronize()
+            break
         for name, bytes_per_env, fns in cases:
             t = timeit(fns)
             try:

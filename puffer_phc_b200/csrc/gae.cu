@@ -11,6 +11,12 @@
 // output is bit-identical to the serial scan; chunks whose window reaches the end of the array are exact by
 // construction.  Tiles are staged in shared memory with coalesced loads/stores (stride-(CH+1) padding).
 // Serial kernel: one thread, used when gamma*lambda is too close to 1 for a bounded window.
+// Pipelined kernel (short windows, K <= 64: PHC's gamma = 0.98, lambda = 0.2 gives K = 32): the same chunked recurrence, but a
+// CTA walks several tiles with the raw arrays of the next two tiles in flight (cp.async, three stages), the per-element terms that do
+// not depend on the carry -- delta and gamma*lambda*nnt, identical for every chunk whose window covers the element -- are computed ONCE
+// per tile by all threads, so a chain step is one 8-byte shared-memory load + FMUL + FADD, and every thread stores its eight
+// advantages straight to global memory (a warp's stores are contiguous).  The one-tile-per-CTA kernel spent its time in load ->
+// barrier -> compute -> barrier -> store round trips with nothing in flight behind them.
 //
 // PRECONDITION of the blocked kernel (mode 0 picks it silently, mode 1 forces it): FINITE inputs.  In the reference's serial scan a
 // NaN / Inf in rewards or values poisons every earlier element up to the previous done; the blocked kernel would carry it only K
@@ -27,8 +33,8 @@ constexpr int GAE_KMAX = 2048;
 // one padding word per CH elements: thread t starts at (CH+1)*t, and CH+1 is odd, so a warp hits 32 distinct banks
 template <int CH> __device__ __forceinline__ int padc(int i) { return i + i / CH; }
 
-// GAE_CH = elements owned by a thread, THREADS = threads per CTA.  CH = 8 for short warm-up windows (the kernel is latency-bound at
-// rollout sizes: many short chains), 32 when the window is long (keeps the redundant warm-up work at K/32 per element).  Tiles are
+// GAE_CH = elements owned by a thread, THREADS = threads per CTA.  This one-tile-per-CTA kernel serves the long windows (K > 64) with
+// CH = 32, which keeps the redundant warm-up work at K/32 per element; short windows go to gae_pipelined_kernel below.  Tiles are
 // staged with 16-byte loads when the three arrays allow it (tile starts are multiples of 4 elements).
 template <int GAE_CH, int THREADS>
 __global__ void __launch_bounds__(THREADS) gae_blocked_kernel(const float* __restrict__ dones, const float* __restrict__ values,
@@ -91,6 +97,128 @@ __global__ void __launch_bounds__(THREADS) gae_blocked_kernel(const float* __res
     }
 }
 
+
+// ---- pipelined kernel for short warm-up windows ---------------------------------------------------------------------------
+__device__ __forceinline__ void gae_cp16(void* smem_dst, const void* gsrc) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void gae_cp4(void* smem_dst, const void* gsrc) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
+}
+constexpr int GAE_STAGES = 3;
+constexpr int GAE_PCH = 8;          // elements per chain thread
+
+__host__ __device__ inline int gae_pipe_rspan(int tile, int K) { return (tile + K + 1 + 3) & ~3; }     // floats per raw array per stage
+__host__ __device__ inline size_t gae_pipe_smem(int tile, int K) {
+    const int span = tile + K + 1;
+    return (size_t)GAE_STAGES * 3 * gae_pipe_rspan(tile, K) * sizeof(float) + (size_t)(span + span / GAE_PCH + 1) * sizeof(float2);
+}
+
+template <int THREADS>
+__global__ void __launch_bounds__(THREADS) gae_pipelined_kernel(const float* __restrict__ dones, const float* __restrict__ values,
+                                                                const float* __restrict__ rewards, int64_t L, float gamma, float gl,
+                                                                int K, float* __restrict__ adv, int vec, int64_t tiles) {
+    extern __shared__ float4 gae_sm4[];
+    constexpr int CH = GAE_PCH, TILE = CH * THREADS;
+    const int span = TILE + K + 1;                     // raw elements [tile0, tile0 + span) feed a tile
+    const int rspan = gae_pipe_rspan(TILE, K);
+    float* raw = reinterpret_cast<float*>(gae_sm4);    // [GAE_STAGES][3][rspan]   dones | values | rewards
+    float2* pairs = reinterpret_cast<float2*>(raw + GAE_STAGES * 3 * rspan);   // [padc(span)]  (delta, gamma*lambda*nnt) per element
+    const int tid = threadIdx.x;
+
+    auto issue = [&](int64_t tile, int stage) {
+        if (tile < tiles) {
+            const int64_t tile0 = tile * TILE;
+            const int avail = (int)((L - tile0 < span) ? (L - tile0) : span);
+            float* sd = raw + stage * 3 * rspan;
+            float* sv = sd + rspan;
+            float* sr = sv + rspan;
+            const int n4 = vec ? (avail >> 2) : 0;
+            for (int q = tid; q < n4; q += THREADS) {
+                gae_cp16(sd + 4 * q, dones + tile0 + 4 * q);
+                gae_cp16(sv + 4 * q, values + tile0 + 4 * q);
+                gae_cp16(sr + 4 * q, rewards + tile0 + 4 * q);
+            }
+            for (int i = 4 * n4 + tid; i < avail; i += THREADS) {
+                gae_cp4(sd + i, dones + tile0 + i);
+                gae_cp4(sv + i, values + tile0 + i);
+                gae_cp4(sr + i, rewards + tile0 + i);
+            }
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");          // one group per pipeline slot, empty past the last tile
+    };
+
+    int64_t tile = blockIdx.x;
+#pragma unroll
+    for (int s = 0; s < GAE_STAGES - 1; ++s) issue(tile + (int64_t)s * gridDim.x, s);
+    for (int it = 0; tile < tiles; tile += gridDim.x, ++it) {
+        const int stage = it % GAE_STAGES;
+        // the stage refilled here was consumed by iteration it - 1, which every thread left through the barrier below
+        issue(tile + (int64_t)(GAE_STAGES - 1) * gridDim.x, (it + GAE_STAGES - 1) % GAE_STAGES);
+        asm volatile("cp.async.wait_group %0;" ::"n"(GAE_STAGES - 1) : "memory");
+        __syncthreads();                               // this tile's raw arrays are visible; the previous tile's chains are done with pairs[]
+        const int64_t tile0 = tile * TILE;
+        const int avail = (int)((L - tile0 < span) ? (L - tile0) : span);
+        const float* sd = raw + stage * 3 * rspan;
+        const float* sv = sd + rspan;
+        const float* sr = sv + rspan;
+        for (int i = tid; i + 1 < avail; i += THREADS) {             // c_gae.pyx:24-27, the part that does not involve the carry
+            const float nnt = 1.0f - sd[i + 1];
+            const float delta = (sr[i + 1] + (gamma * sv[i + 1]) * nnt) - sv[i];
+            pairs[padc<CH>(i)] = make_float2(delta, gl * nnt);
+        }
+        __syncthreads();
+        const int c0 = tid * CH;
+        const int64_t g0 = tile0 + c0;
+        if (g0 < L) {
+            int64_t hi = g0 + CH - 1 + K;              // warm-up start, clipped to L-2 (adv[L-1] = 0 starts the true scan)
+            if (hi > L - 2) hi = L - 2;
+            float last = 0.0f;
+            int i = (int)(hi - tile0);
+            // warm-up: groups of CH steps with the CH loads issued ahead of the dependent FMUL / FADD chain (an unclipped window starts
+            // on the last element of a padding group, so the CH offsets are compile-time constants)
+            for (; i - (CH - 1) >= c0 + CH && (i & (CH - 1)) == CH - 1; i -= CH) {
+                const float2* pp = pairs + padc<CH>(i - (CH - 1));
+                float2 p[CH];
+#pragma unroll
+                for (int u = 0; u < CH; ++u) p[u] = pp[u];
+#pragma unroll
+                for (int u = CH - 1; u >= 0; --u) last = p[u].x + p[u].y * last;               // c_gae.pyx:28
+            }
+            for (; i >= c0 + CH; --i) {
+                const float2 p = pairs[padc<CH>(i)];
+                last = p.x + p.y * last;
+            }
+            float o[CH];
+            {
+                const float2* pp = pairs + padc<CH>(c0);            // the chunk is one padding group: CH consecutive pairs
+                float2 p[CH];
+#pragma unroll
+                for (int k = 0; k < CH; ++k) p[k] = pp[k];          // (slots past L-2 hold stale values that are never used)
+#pragma unroll
+                for (int k = CH - 1; k >= 0; --k) {
+                    if (g0 + k <= L - 2) {
+                        last = p[k].x + p[k].y * last;
+                        o[k] = last;
+                    } else {
+                        o[k] = 0.0f;                   // adv[L-1]
+                    }
+                }
+            }
+            if (vec && g0 + CH <= L) {
+                float4* o4 = reinterpret_cast<float4*>(adv + g0);
+                o4[0] = make_float4(o[0], o[1], o[2], o[3]);
+                o4[1] = make_float4(o[4], o[5], o[6], o[7]);
+            } else {
+#pragma unroll
+                for (int k = 0; k < CH; ++k)
+                    if (g0 + k < L) adv[g0 + k] = o[k];
+            }
+        }
+    }
+    asm volatile("cp.async.wait_all;" ::: "memory");
+}
+
 // one warp: coalesced staging of 1024-element chunks, lane 0 runs the recurrence.
 constexpr int GAE_SER_CHUNK = 1024;
 __global__ void __launch_bounds__(32) gae_serial_kernel(const float* __restrict__ dones, const float* __restrict__ values,
@@ -150,23 +278,34 @@ extern "C" int phc_gae(const float* dones, const float* values, const float* rew
         gae_serial_kernel<<<1, 32, 0, s>>>(dones, values, rewards, L, gamma, gl, advantages);
         return check_launch(fn);
     }
-    const int ch = (K <= 64) ? 8 : 32;
-#ifndef GAE_T8
-#define GAE_T8 256                                     // threads per CTA of the CH = 8 instantiation (A/B: 64 / 128 / 256)
-#endif
-    const int threads = ch == 8 ? GAE_T8 : GAE_THREADS;
-    const int tile = ch * threads;
-    const int span = tile + K + 1;
-    const size_t smem = (size_t)(3 * ((span + span / ch) + 1) + (tile + tile / ch) + 1) * sizeof(float);
-    const int64_t tiles = (L + tile - 1) / tile;
     const int vec = aligned16(dones) && aligned16(values) && aligned16(rewards) && aligned16(advantages);
-    if (ch == 8) {
-        if (smem > 48 * 1024) {
-            cudaError_t e = cudaFuncSetAttribute(gae_blocked_kernel<8, GAE_T8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (K <= 64) {
+        // short window: the pipelined kernel.  2048-element tiles once there are two per SM, else 512-element tiles (more CTAs in
+        // flight for rollouts that do not fill the GPU); CTAs walk equal numbers of tiles.
+        const int sms = sm_count();
+        const bool big = (L + 2047) / 2048 >= 2 * (int64_t)sms;
+        const int tile = big ? 2048 : 512;
+        const size_t smem = gae_pipe_smem(tile, K);
+        const int64_t tiles = (L + tile - 1) / tile;
+        const int64_t resident = (int64_t)sms * (big ? 2 : 8);
+        const int64_t per = (tiles + resident - 1) / resident;
+        const unsigned grid = (unsigned)((tiles + per - 1) / per);
+        if (big) {
+            cudaError_t e = cudaFuncSetAttribute(gae_pipelined_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
             if (e != cudaSuccess) return fail((int)e, "%s: cudaFuncSetAttribute: %s", fn, cudaGetErrorString(e));
+            gae_pipelined_kernel<256><<<grid, 256, smem, s>>>(dones, values, rewards, L, gamma, gl, K, advantages, vec, tiles);
+        } else {
+            gae_pipelined_kernel<64><<<grid, 64, smem, s>>>(dones, values, rewards, L, gamma, gl, K, advantages, vec, tiles);
         }
-        gae_blocked_kernel<8, GAE_T8><<<(unsigned)tiles, GAE_T8, smem, s>>>(dones, values, rewards, L, gamma, gl, K, advantages, vec);
-    } else {
+        return check_launch(fn);
+    }
+    {
+        const int ch = 32;
+        const int threads = GAE_THREADS;
+        const int tile = ch * threads;
+        const int span = tile + K + 1;
+        const size_t smem = (size_t)(3 * ((span + span / ch) + 1) + (tile + tile / ch) + 1) * sizeof(float);
+        const int64_t tiles = (L + tile - 1) / tile;
         if (smem > 48 * 1024) {      // per-device attribute and a cheap call: set it on every launch that needs it (no per-thread cache)
             cudaError_t e = cudaFuncSetAttribute(gae_blocked_kernel<32, GAE_THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
             if (e != cudaSuccess) return fail((int)e, "%s: cudaFuncSetAttribute: %s", fn, cudaGetErrorString(e));

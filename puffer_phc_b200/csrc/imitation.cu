@@ -16,7 +16,10 @@ namespace phc {
 
 constexpr int IM_WARPS = 4;
 
-__device__ __forceinline__ const float* at(const phc_view& v, int64_t n, int j) { return v.ptr + n * v.stride_env + (int64_t)j * v.stride_body; }
+// kernel-side copy of a phc_view with the body stride as a 32-bit int: a lane address is one wide multiply-add on top of the env's base
+// instead of a 64-bit multiplication per view (the stand-alone kernels are instruction-issue-bound, not memory-bound)
+struct KView { const float* ptr; int64_t stride_env; int stride_body; };
+__device__ __forceinline__ const float* at(const KView& v, int64_t n, int j) { return v.ptr + n * v.stride_env + j * v.stride_body; }
 
 // .mean(dim=-1) over the J <= 32 lane values d in torch's summation order for the chosen device (phc_math.cuh mean_ordered); the
 // result is valid in every lane.  Only the eval-mode paths (use_mean, mpjpe) come here.
@@ -44,7 +47,7 @@ __device__ __forceinline__ BodyState body_from_record(const float* s, int j) {
 }
 
 struct ObsArgs {
-    phc_view root_pos, root_rot, pos, rot, vel, ang, rpos, rrot, rvel, rang;
+    KView root_pos, root_rot, pos, rot, vel, ang, rpos, rrot, rvel, rang;
     int64_t N; int J; int upright; float* obs; int64_t obs_stride;
 };
 
@@ -68,12 +71,12 @@ __global__ void __launch_bounds__(IM_WARPS * 32) imitation_obs_kernel(const ObsA
     const BodyState b = AOS ? body_from_record(rec, j)
                             : BodyState{ld3(at(a.pos, n, j)), ld4(at(a.rot, n, j)), ld3(at(a.vel, n, j)), ld3(at(a.ang, n, j))};
     float* o = a.obs + n * a.obs_stride;
-    task_obs_body(b, r, rp, hz, hw, o + 3 * j, o + 3 * J + 6 * j, o + 9 * J + 3 * j, o + 12 * J + 3 * j, o + 15 * J + 3 * j,
-                  o + 18 * J + 6 * j);
+    task_obs_body_fma(b, r, rp, hz, hw, zrot_make(hz, hw), o + 3 * j, o + 3 * J + 6 * j, o + 9 * J + 3 * j, o + 12 * J + 3 * j,
+                      o + 15 * J + 3 * j, o + 18 * J + 6 * j);
 }
 
 struct SelfArgs {
-    phc_view pos, rot, vel, ang;
+    KView pos, rot, vel, ang;
     int64_t N; int J; int local_root_obs, root_height_obs, upright; float* obs; int64_t obs_stride;
 };
 
@@ -97,13 +100,15 @@ __global__ void __launch_bounds__(IM_WARPS * 32) self_obs_kernel(const SelfArgs 
     const BodyState b = AOS ? body_from_record(rec, j)
                             : BodyState{ld3(at(a.pos, n, j)), ld4(at(a.rot, n, j)), ld3(at(a.vel, n, j)), ld3(at(a.ang, n, j))};
     float* rot_out = o + 3 * (J - 1) + 6 * j;
-    self_obs_body(b, rp, hz, hw, j, o + 3 * (j - 1), rot_out, o + 3 * (J - 1) + 6 * J + 3 * j, o + 3 * (J - 1) + 9 * J + 3 * j);
+    const ZRot hrot = zrot_make(hz, hw);
+    self_obs_pos_rot_fma(b, rp, hz, hw, hrot, j, o + 3 * (j - 1), rot_out);
+    self_obs_vel_ang_fma(b, hrot, o + 3 * (J - 1) + 6 * J + 3 * j, o + 3 * (J - 1) + 9 * J + 3 * j);
     if (!a.local_root_obs && j == 0) tan_norm(rr, rot_out);      // common.py:77-79
 }
 
 struct RewardArgs {
-    phc_view pos, rot, vel, ang, rpos, rrot, rvel, rang;
-    int64_t N; int J; float k[4], w[4]; float* reward; float* raw; int64_t raw_stride;
+    KView pos, rot, vel, ang, rpos, rrot, rvel, rang;
+    int64_t N; int J; float k[4], w[4]; float inv3j, invj; float* reward; float* raw; int64_t raw_stride;
 };
 
 template <bool AOS>
@@ -121,19 +126,22 @@ __global__ void __launch_bounds__(IM_WARPS * 32) reward_kernel(const RewardArgs 
         const int j = lane;
         const BodyState b = AOS ? body_from_record(rec, j)
                                 : BodyState{ld3(at(a.pos, n, j)), ld4(at(a.rot, n, j)), ld3(at(a.vel, n, j)), ld3(at(a.ang, n, j))};
-        reward_terms_body(b, r, sp, sr, sv, sa);
+        reward_terms_body_fma(b, r, sp, sr, sv, sa);           // sums of squares + closed-form squared angle, as in the fused step
     }
     sp = warp_sum(sp); sr = warp_sum(sr); sv = warp_sum(sv); sa = warp_sum(sa);
+    // env-level tail (common.py:300-320): lane v < 4 evaluates exponential kernel v, lane 0 collects -- four expf side by side
+    float val = lane == 0 ? sp * a.inv3j : lane == 1 ? sr * a.invj : lane == 2 ? sv * a.inv3j : sa * a.inv3j;
+    val = expf(-a.k[lane & 3] * val);
+    const float r0 = __shfl_sync(FULL, val, 0), r1 = __shfl_sync(FULL, val, 1), r2 = __shfl_sync(FULL, val, 2), r3 = __shfl_sync(FULL, val, 3);
     if (lane == 0) {
-        float raw[4];
-        a.reward[n] = reward_from_sums(sp, sr, sv, sa, (float)a.J, a.k, a.w, raw);
+        a.reward[n] = ((a.w[0] * r0 + a.w[1] * r1) + a.w[2] * r2) + a.w[3] * r3;
         float* o = a.raw + n * a.raw_stride;
-        o[0] = raw[0]; o[1] = raw[1]; o[2] = raw[2]; o[3] = raw[3];
+        o[0] = r0; o[1] = r1; o[2] = r2; o[3] = r3;
     }
 }
 
 struct ResetArgs {
-    const int16_t* progress; phc_view pos, rpos; const uint8_t* pass_time; int early; const float* term_dist; int use_mean;
+    const int16_t* progress; KView pos, rpos; const uint8_t* pass_time; int early; const float* term_dist; int use_mean;
     int64_t N; int J; uint8_t* reset; uint8_t* terminated; int dev;
 };
 
@@ -165,7 +173,7 @@ __global__ void __launch_bounds__(IM_WARPS * 32) reset_kernel(const ResetArgs a)
 
 // Evaluation metric of HumanoidPHC.step (reference puffer_phc/envs/humanoid_phc.py:159-163):
 // mpjpe = (body_pos - rg_pos).norm(dim=-1).mean(dim=-1).  One warp per env, lane = body.
-struct MpjpeArgs { phc_view pos, rpos; int64_t N; int J; float* out; int dev; };
+struct MpjpeArgs { KView pos, rpos; int64_t N; int J; float* out; int dev; };
 
 __global__ void __launch_bounds__(IM_WARPS * 32) mpjpe_kernel(const MpjpeArgs a) {
     const int lane = threadIdx.x & 31;
@@ -239,8 +247,11 @@ __global__ void __launch_bounds__(IM_WARPS * 32) amp_obs_kernel(const AmpArgs a)
 
 static int check_view(const char* fn, const char* name, const phc_view& v) {
     if (!v.ptr) return fail(PHC_EINVAL, "%s: %s is NULL", fn, name);
+    if (v.stride_body >= (1 << 26) || v.stride_body <= -(1 << 26))
+        return fail(PHC_EUNSUPPORTED, "%s: %s.stride_body=%lld (bodies of one env must lie within 2^26 floats of each other)", fn, name, (long long)v.stride_body);
     return PHC_OK;
 }
+static KView kv(const phc_view& v) { return KView{v.ptr, v.stride_env, (int)v.stride_body}; }
 
 // the four views are the pos | rot | vel | ang-vel slices of one 13-float record per body (humanoid_phc.py:546-549)
 static bool is_aos_record(const phc_view& p, const phc_view& r, const phc_view& v, const phc_view& w) {
@@ -269,8 +280,8 @@ extern "C" int phc_imitation_obs_v6(phc_view root_pos, phc_view root_rot, phc_vi
     CHECK_VIEW(fn, ref_body_vel); CHECK_VIEW(fn, ref_body_ang_vel);
     PHC_REQUIRE(obs, PHC_EINVAL, "%s: obs is NULL", fn);
     PHC_REQUIRE(obs_stride >= 24 * J, PHC_ESHAPE, "%s: obs_stride=%lld < 24*J", fn, (long long)obs_stride);
-    ObsArgs a{root_pos, root_rot, body_pos, body_rot, body_vel, body_ang_vel, ref_body_pos, ref_body_rot, ref_body_vel,
-              ref_body_ang_vel, N, J, upright, obs, obs_stride};
+    ObsArgs a{kv(root_pos), kv(root_rot), kv(body_pos), kv(body_rot), kv(body_vel), kv(body_ang_vel), kv(ref_body_pos), kv(ref_body_rot),
+              kv(ref_body_vel), kv(ref_body_ang_vel), N, J, upright, obs, obs_stride};
     const unsigned grid = (unsigned)((N + IM_WARPS - 1) / IM_WARPS);
     if (is_aos_record(body_pos, body_rot, body_vel, body_ang_vel)) imitation_obs_kernel<true><<<grid, IM_WARPS * 32, 0, (cudaStream_t)stream>>>(a);
     else imitation_obs_kernel<false><<<grid, IM_WARPS * 32, 0, (cudaStream_t)stream>>>(a);
@@ -287,7 +298,7 @@ extern "C" int phc_self_obs_smpl_max(phc_view body_pos, phc_view body_rot, phc_v
     CHECK_VIEW(fn, body_pos); CHECK_VIEW(fn, body_rot); CHECK_VIEW(fn, body_vel); CHECK_VIEW(fn, body_ang_vel);
     PHC_REQUIRE(obs, PHC_EINVAL, "%s: obs is NULL", fn);
     PHC_REQUIRE(obs_stride >= (root_height_obs ? 1 : 0) + 3 * (J - 1) + 12 * J, PHC_ESHAPE, "%s: obs_stride too small", fn);
-    SelfArgs a{body_pos, body_rot, body_vel, body_ang_vel, N, J, local_root_obs, root_height_obs, upright, obs, obs_stride};
+    SelfArgs a{kv(body_pos), kv(body_rot), kv(body_vel), kv(body_ang_vel), N, J, local_root_obs, root_height_obs, upright, obs, obs_stride};
     const unsigned grid = (unsigned)((N + IM_WARPS - 1) / IM_WARPS);
     if (is_aos_record(body_pos, body_rot, body_vel, body_ang_vel)) self_obs_kernel<true><<<grid, IM_WARPS * 32, 0, (cudaStream_t)stream>>>(a);
     else self_obs_kernel<false><<<grid, IM_WARPS * 32, 0, (cudaStream_t)stream>>>(a);
@@ -341,12 +352,16 @@ extern "C" int phc_imitation_reward(phc_view body_pos, phc_view body_rot, phc_vi
     CHECK_VIEW(fn, ref_body_pos); CHECK_VIEW(fn, ref_body_rot); CHECK_VIEW(fn, ref_body_vel); CHECK_VIEW(fn, ref_body_ang_vel);
     PHC_REQUIRE(k_h && w_h && reward && reward_raw, PHC_EINVAL, "%s: NULL pointer", fn);
     PHC_REQUIRE(raw_stride >= 4, PHC_ESHAPE, "%s: raw_stride < 4", fn);
-    RewardArgs a{body_pos, body_rot, body_vel, body_ang_vel, ref_body_pos, ref_body_rot, ref_body_vel, ref_body_ang_vel, N, J,
-                 {k_h[0], k_h[1], k_h[2], k_h[3]}, {w_h[0], w_h[1], w_h[2], w_h[3]}, reward, reward_raw, raw_stride};
+    RewardArgs a{kv(body_pos), kv(body_rot), kv(body_vel), kv(body_ang_vel), kv(ref_body_pos), kv(ref_body_rot), kv(ref_body_vel),
+                 kv(ref_body_ang_vel), N, J,
+                 {k_h[0], k_h[1], k_h[2], k_h[3]}, {w_h[0], w_h[1], w_h[2], w_h[3]}, 1.0f / (3.0f * (float)J), 1.0f / (float)J, reward,
+                 reward_raw, raw_stride};
     const unsigned grid = (unsigned)((N + IM_WARPS - 1) / IM_WARPS);
-    // (the AOS instantiation measured slower here -- 38.9 vs 37.6 us at 65536 envs even with the reference loads issued first:
-    // too little math to hide the staging round trip)
-    reward_kernel<false><<<grid, IM_WARPS * 32, 0, (cudaStream_t)stream>>>(a);
+#ifndef IM_REWARD_AOS
+#define IM_REWARD_AOS 0          // A/B builds: 1 = stage the AoS record through shared memory as the observation kernels do
+#endif
+    if (IM_REWARD_AOS && is_aos_record(body_pos, body_rot, body_vel, body_ang_vel)) reward_kernel<true><<<grid, IM_WARPS * 32, 0, (cudaStream_t)stream>>>(a);
+    else reward_kernel<false><<<grid, IM_WARPS * 32, 0, (cudaStream_t)stream>>>(a);
     return check_launch(fn);
 }
 
@@ -361,7 +376,7 @@ extern "C" int phc_im_reset(const int16_t* progress, phc_view rigid_body_pos, ph
     PHC_REQUIRE(progress && pass_time && reset && terminated, PHC_EINVAL, "%s: NULL pointer", fn);
     PHC_REQUIRE(!enable_early_termination || termination_distance, PHC_EINVAL, "%s: termination_distance is NULL", fn);
     PHC_REQUIRE(ref_device == PHC_REF_DEVICE_CPU || ref_device == PHC_REF_DEVICE_CUDA, PHC_EINVAL, "%s: ref_device must be 0 or 1", fn);
-    ResetArgs a{progress, rigid_body_pos, ref_body_pos, pass_time, enable_early_termination, termination_distance, use_mean,
+    ResetArgs a{progress, kv(rigid_body_pos), kv(ref_body_pos), pass_time, enable_early_termination, termination_distance, use_mean,
                 N, J, reset, terminated, ref_device};
     const unsigned grid = (unsigned)((N + IM_WARPS - 1) / IM_WARPS);
     // (staging the whole record span measured slower -- 27.8 vs 17.2 us: the strided loads touch only the position sectors)
@@ -376,7 +391,7 @@ extern "C" int phc_mpjpe(phc_view body_pos, phc_view ref_body_pos, int64_t N, in
     if (N == 0) return PHC_OK;
     CHECK_VIEW(fn, body_pos); CHECK_VIEW(fn, ref_body_pos);
     PHC_REQUIRE(mpjpe, PHC_EINVAL, "%s: NULL pointer", fn);
-    MpjpeArgs a{body_pos, ref_body_pos, N, J, mpjpe, ref_device};
+    MpjpeArgs a{kv(body_pos), kv(ref_body_pos), N, J, mpjpe, ref_device};
     mpjpe_kernel<<<(unsigned)((N + IM_WARPS - 1) / IM_WARPS), IM_WARPS * 32, 0, (cudaStream_t)stream>>>(a);
     return check_launch(fn);
 }

@@ -334,10 +334,13 @@ __global__ void __launch_bounds__(AR_TWARPS * 32) auto_reset_tail_kernel(const A
         heading_quat(calc_heading(root_q), hz, hw);
         if (j < NB) {
             if (j == 0) row[0] = root_p.z;                                                                 // common.py:40
-            self_obs_body(b, root_p, hz, hw, j, row + 1 + 3 * (j - 1), row + 70 + 6 * j, row + 214 + 3 * j, row + 286 + 3 * j);
+            // the same per-body arithmetic as the stand-alone observation kernels (imitation.cu) and the fused step
+            const ZRot hrot = zrot_make(hz, hw);
+            self_obs_pos_rot_fma(b, root_p, hz, hw, hrot, j, row + 1 + 3 * (j - 1), row + 70 + 6 * j);
+            self_obs_vel_ang_fma(b, hrot, row + 214 + 3 * j, row + 286 + 3 * j);
             float* q = row + OBS_SELF;
-            task_obs_body(b, ref, root_p, hz, hw, q + 3 * j, q + 72 + 6 * j, q + 216 + 3 * j, q + 288 + 3 * j, q + 360 + 3 * j,
-                          q + 432 + 6 * j);
+            task_obs_body_fma(b, ref, root_p, hz, hw, hrot, q + 3 * j, q + 72 + 6 * j, q + 216 + 3 * j, q + 288 + 3 * j, q + 360 + 3 * j,
+                              q + 432 + 6 * j);
         }
         __syncwarp();
 #pragma unroll

@@ -121,6 +121,9 @@ constexpr int ST_WBUF_F = ST_AUX_OFF + ST_AUX_F;     // per (env, role): sim rec
                                                      // bit-identical, measured 0.1683 vs 0.1677 ms: role A's lateness is not what
                                                      // the writers wait for
 #endif
+#ifndef ST_BALANCE
+#define ST_BALANCE 1                                 // 0: always fill all ST_SLOTS slots of a block (A/B builds)
+#endif
 #ifndef ST_USE_AUX
 #define ST_USE_AUX 1                                 // 0: ignore the motion library's pair tables (A/B builds)
 #endif
@@ -151,8 +154,10 @@ struct StepArgs {
     phc_step_out out;
     int sim_vec;          // body_state rows are 16-byte aligned -> 16-byte cp.async staging
     int obs_vec;          // obs tiles are contiguous and 16-byte aligned -> TMA bulk tile stores
-    int64_t num_blocks;   // ceil(N / S)
+    int64_t num_blocks;   // ceil(N / epb)
     int use_aux;          // the motion library's pair tables exist and were built for cfg.ref_device
+    int epb;              // envs per block (even, <= ST_ENVS): small batches are spread evenly over the CTAs' iterations instead of
+                          // filling 12 slots on some SMs and none on others; slots >= epb idle
 };
 
 // ---- async-copy / barrier primitives ------------------------------------------------------------------------
@@ -399,15 +404,15 @@ __global__ void __maxnreg__(ST_MAXREG) step_fused_kernel(const StepArgs a) {   /
         if ((int64_t)blockIdx.x < a.num_blocks) {
             mbar_wait<ST_CHINT>(&pfull[0], 0);
             cur = plans[buf];
-            if (cur.valid & 1) issue_env<PACKED>(a, cur, (int64_t)blockIdx.x * ST_ENVS + slot, role, wbuf, j, &lfull[buf]);
+            if (cur.valid & 1) issue_env<PACKED>(a, cur, (int64_t)blockIdx.x * a.epb + slot, role, wbuf, j, &lfull[buf]);
         }
         cp_async_commit();
         int it = 0;
         const float my_term_dist = __ldg(in.term_dist + j);       // this lane's body never changes
         PROF_DECL
         for (int64_t blk = blockIdx.x; blk < a.num_blocks; blk += gridDim.x, ++it) {
-            const int64_t e = blk * ST_ENVS + slot;
-            const bool valid = e < in.N;
+            const int64_t e = blk * a.epb + slot;
+            const bool valid = slot < a.epb && e < in.N;
             const int b = it % ST_TILES, use = it / ST_TILES;                  // use-th time tile buffer b is filled
             float* my_tile = tiles + (b * ST_ENVS + slot) * OBS_W;
 
@@ -466,7 +471,7 @@ __global__ void __maxnreg__(ST_MAXREG) step_fused_kernel(const StepArgs a) {   /
                     else mbar_wait<ST_CHINT>(&pfull[d], ((it + 1) / ST_PLANS) & 1);
                     PROF_END(1)
                     nxt = plans[d * ST_NBUF + buf];
-                    if (nxt.valid & 1) issue_env<PACKED>(a, nxt, nblk * ST_ENVS + slot, role, wbuf, j, &lfull[buf]);
+                    if (nxt.valid & 1) issue_env<PACKED>(a, nxt, nblk * a.epb + slot, role, wbuf, j, &lfull[buf]);
                 }
                 cp_async_commit();
             }
@@ -645,8 +650,8 @@ __global__ void __maxnreg__(ST_MAXREG) step_fused_kernel(const StepArgs a) {   /
         for (int64_t blk = blockIdx.x; blk < a.num_blocks; blk += gridDim.x, ++it) {
             const int b = it % ST_TILES;
             const float* tile = tiles + b * ST_ENVS * OBS_W;
-            const int64_t e0 = blk * ST_ENVS;
-            const int rows = (int)((in.N - e0 < ST_ENVS) ? (in.N - e0) : ST_ENVS);
+            const int64_t e0 = blk * a.epb;
+            const int rows = (int)((in.N - e0 < a.epb) ? (in.N - e0) : a.epb);
             mbar_wait<ST_WHINT>(&full[b], (it / ST_TILES) & 1);
 #if !ST_SPLIT_DONE
             if (do_met) {
@@ -718,9 +723,9 @@ __global__ void __maxnreg__(ST_MAXREG) step_fused_kernel(const StepArgs a) {   /
         for (int64_t blk = blockIdx.x; blk < a.num_blocks; blk += gridDim.x, ++p) {
 #if ST_PLAN_EARLY
             // the plan is computed (its two dependent load latencies paid) BEFORE the wait for the ring slot
-            const int64_t e = blk * ST_ENVS + lane % ST_ENVS;
+            const int64_t e = blk * a.epb + lane % ST_ENVS;
             EnvPlan pl{};
-            if (lane < ST_NBUF) pl = make_plan(a, e, lane / ST_ENVS);
+            if (lane < ST_NBUF && lane % ST_ENVS < a.epb) pl = make_plan(a, e, lane / ST_ENVS);
 #endif
             if (p >= ST_PLANS - 1) {
                 const int q = p - (ST_PLANS - 1);
@@ -730,8 +735,9 @@ __global__ void __maxnreg__(ST_MAXREG) step_fused_kernel(const StepArgs a) {   /
             const int d = p % ST_PLANS;
             if (lane < ST_NBUF) {
 #if !ST_PLAN_EARLY
-                const int64_t e = blk * ST_ENVS + lane % ST_ENVS;
-                const EnvPlan pl = make_plan(a, e, lane / ST_ENVS);
+                const int64_t e = blk * a.epb + lane % ST_ENVS;
+                EnvPlan pl{};
+                if (lane % ST_ENVS < a.epb) pl = make_plan(a, e, lane / ST_ENVS);
 #endif
                 plans[d * ST_NBUF + lane] = pl;
 #if ST_PREFETCH
@@ -789,7 +795,17 @@ extern "C" int phc_step_fused(const phc_motion_tables* t, const phc_step_in* in,
     }
     // the grid is fixed (one persistent CTA per SM) so that the number of moment partial slots does not depend on N
     const int grid = phc_step_num_partials();
-    StepArgs a{*t, *in, *cfg, *out, 0, 0, (in->N + ST_ENVS - 1) / ST_ENVS, 0};
+    // envs per block: the CTAs' iteration count is that of full 12-env blocks; the envs are then spread evenly over grid x iterations
+    // block slots (4096 envs: 3 iterations of 10 on every SM instead of 3 x 12 on 46 SMs and 2 x 12 on the rest)
+    int epb = ST_ENVS;
+    if (ST_BALANCE && in->N > 0) {
+        const int64_t blocks_full = (in->N + ST_ENVS - 1) / ST_ENVS;
+        const int64_t iters = (blocks_full + grid - 1) / grid;
+        int64_t per = (in->N + grid * iters - 1) / (grid * iters);
+        per = (per + 1) & ~(int64_t)1;
+        epb = (int)(per < 2 ? 2 : per > ST_ENVS ? ST_ENVS : per);
+    }
+    StepArgs a{*t, *in, *cfg, *out, 0, 0, (in->N + epb - 1) / epb, 0, epb};
     a.sim_vec = aligned16(in->body_state) && (in->env_stride % 4 == 0);
     a.obs_vec = out->obs_stride == OBS_W && aligned16(out->obs) && (!out->obs_norm || aligned8(out->obs_norm));
     if (in->N == 0 && !out->moment_partials) return PHC_OK;

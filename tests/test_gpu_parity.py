@@ -263,6 +263,27 @@ def test_gae_full_size_vs_oracle(gam, lam):
         assert_equal(got.view(np.uint32), ref_gae.compute_gae(d, v, r, gam, lam).view(np.uint32), "vs reference c_gae")
 
 
+@pytest.mark.parametrize("gam,lam", [(0.98, 0.2), (0.9, 0.5), (0.0, 0.5)])
+def test_gae_pipelined_many_tiles_ragged_and_unaligned(gam, lam):
+    """The short-window kernel where a CTA walks several tiles (65536 x 32), lengths that end inside a tile / a chunk / a 16-byte
+    group, and array slices that are not 16-byte aligned (4-byte staging, scalar stores): bit-exact against the serial scan."""
+    from oracle import c_oracle as co
+    from puffer_phc_b200 import c_gae, synth
+    R = synth.make_rollout(65536, 32, seed=11, p_done=0.01)
+    d, v, r = (R[k].numpy() for k in ("dones", "values", "rewards"))
+    dc, vc, rc = cu(d), cu(v), cu(r)
+    for L in (65536 * 32, 65536 * 32 - 3, 2048 * 296 + 1, 2048 * 296, 2048 * 300 + 2047, 511, 513, 9, 2, 1):
+        want = co.gae(d[:L], v[:L], r[:L], gam, lam)
+        got = npy(c_gae.compute_gae_cuda(dc[:L], vc[:L], rc[:L], gam, lam))
+        assert_equal(got.view(np.uint32), want.view(np.uint32), f"gae L={L} gamma={gam} lambda={lam}")
+    for off, L in ((1, 700001), (3, 4097), (2, 700)):
+        want = co.gae(d[off:off + L], v[off:off + L], r[off:off + L], gam, lam)
+        out = torch.full((L + 8,), -7.0, device=DEV)
+        got = c_gae.compute_gae_cuda(dc[off:off + L], vc[off:off + L], rc[off:off + L], gam, lam, out=out[off:off + L])
+        assert_equal(npy(got).view(np.uint32), want.view(np.uint32), f"gae unaligned off={off} L={L}")
+        assert torch.all(out[:off] == -7.0) and torch.all(out[off + L:] == -7.0), "stores outside the output slice"
+
+
 def test_sample_time_interval(golden):
     S, T = golden["sample_time"], golden["synth_tables"]
     lib = make_lib(T)
