@@ -11,12 +11,8 @@
 // output is bit-identical to the serial scan; chunks whose window reaches the end of the array are exact by
 // construction.  Tiles are staged in shared memory with coalesced loads/stores (stride-(CH+1) padding).
 // Serial kernel: one thread, used when gamma*lambda is too close to 1 for a bounded window.
-// Pipelined kernel (short windows, K <= 64: PHC's gamma = 0.98, lambda = 0.2 gives K = 32): the same chunked recurrence, but a
-// CTA walks several tiles with the raw arrays of the next two tiles in flight (cp.async, three stages), the per-element terms that do
-// not depend on the carry -- delta and gamma*lambda*nnt, identical for every chunk whose window covers the element -- are computed ONCE
-// per tile by all threads, so a chain step is one 8-byte shared-memory load + FMUL + FADD, and every thread stores its eight
-// advantages straight to global memory (a warp's stores are contiguous).  The one-tile-per-CTA kernel spent its time in load ->
-// barrier -> compute -> barrier -> store round trips with nothing in flight behind them.
+// Direct kernel (short windows, K <= 64: PHC's gamma = 0.98, lambda = 0.2 gives K = 32): the same chunked recurrence without staging
+// the raw arrays -- see gae_direct_kernel.
 //
 // PRECONDITION of the blocked kernel (mode 0 picks it silently, mode 1 forces it): FINITE inputs.  In the reference's serial scan a
 // NaN / Inf in rewards or values poisons every earlier element up to the previous done; the blocked kernel would carry it only K
@@ -34,7 +30,7 @@ constexpr int GAE_KMAX = 2048;
 template <int CH> __device__ __forceinline__ int padc(int i) { return i + i / CH; }
 
 // GAE_CH = elements owned by a thread, THREADS = threads per CTA.  This one-tile-per-CTA kernel serves the long windows (K > 64) with
-// CH = 32, which keeps the redundant warm-up work at K/32 per element; short windows go to gae_pipelined_kernel below.  Tiles are
+// CH = 32, which keeps the redundant warm-up work at K/32 per element; short windows go to gae_direct_kernel below.  Tiles are
 // staged with 16-byte loads when the three arrays allow it (tile starts are multiples of 4 elements).
 template <int GAE_CH, int THREADS>
 __global__ void __launch_bounds__(THREADS) gae_blocked_kernel(const float* __restrict__ dones, const float* __restrict__ values,
@@ -98,125 +94,136 @@ __global__ void __launch_bounds__(THREADS) gae_blocked_kernel(const float* __res
 }
 
 
-// ---- pipelined kernel for short warm-up windows ---------------------------------------------------------------------------
-__device__ __forceinline__ void gae_cp16(void* smem_dst, const void* gsrc) {
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
-}
-__device__ __forceinline__ void gae_cp4(void* smem_dst, const void* gsrc) {
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
-}
-constexpr int GAE_STAGES = 3;
-constexpr int GAE_PCH = 8;          // elements per chain thread
+// (delta, coefficient) pairs live in groups of CH with two pad pairs behind each group: a chain thread's group starts 8 * (CH + 2) bytes
+// after its neighbour's -- an odd number of 16-byte units for CH = 8 and 16, so the 16-byte loads of a quarter warp hit distinct
+// banks -- and groups of four elements stay 16-byte aligned for the precompute pass's stores.
+template <int CH> __host__ __device__ __forceinline__ int padp(int i) { return i + 2 * (i / CH); }
 
-__host__ __device__ inline int gae_pipe_rspan(int tile, int K) { return (tile + K + 1 + 3) & ~3; }     // floats per raw array per stage
-__host__ __device__ inline size_t gae_pipe_smem(int tile, int K) {
-    const int span = tile + K + 1;
-    return (size_t)GAE_STAGES * 3 * gae_pipe_rspan(tile, K) * sizeof(float) + (size_t)(span + span / GAE_PCH + 1) * sizeof(float2);
+// c_gae.pyx:24-27, the part of a step that does not involve the carry: element i needs dones / rewards / values at i + 1 and values at i
+__device__ __forceinline__ float2 gae_pair(float d1, float v1, float r1, float v0, float gamma, float gl) {
+    const float nnt = 1.0f - d1;
+    return make_float2((r1 + (gamma * v1) * nnt) - v0, gl * nnt);
 }
 
-template <int THREADS>
-__global__ void __launch_bounds__(THREADS) gae_pipelined_kernel(const float* __restrict__ dones, const float* __restrict__ values,
-                                                                const float* __restrict__ rewards, int64_t L, float gamma, float gl,
-                                                                int K, float* __restrict__ adv, int vec, int64_t tiles) {
+// ---- direct kernel for short warm-up windows ------------------------------------------------------------------------------------
+// Staged variants of this kernel (the one-tile-per-CTA kernel above with 8-element chunks; a persistent cp.async-pipelined kernel with
+// 2 or 3 stages, 8- or 16-element chunks, 8 to 24 warps per SM) all measured 10-13 us for 65536 x 32 whatever their occupancy and
+// instruction count: they move ~75 bytes per element through SHARED memory (raw arrays in, raw arrays out again for the pairs, five
+// chain reads per element), which at 128 B/clk per SM is the whole run time (profiles/README.md).  This kernel touches shared memory
+// only with the pairs (8.0 us):
+// global -> registers (16-byte loads, the element behind a group of four comes from the neighbour lane) -> (delta, coefficient) pairs in
+// shared memory (8 B per element, written once) -> chains of CH = 16 elements (3 x 8 B read per element) -> advantages from registers
+// straight to global memory.
+template <int CH, int THREADS, int TILE>
+__global__ void __launch_bounds__(THREADS) gae_direct_kernel(const float* __restrict__ dones, const float* __restrict__ values,
+                                                             const float* __restrict__ rewards, int64_t L, float gamma, float gl,
+                                                             int K, float* __restrict__ adv, int vec) {
     extern __shared__ float4 gae_sm4[];
-    constexpr int CH = GAE_PCH, TILE = CH * THREADS;
-    const int span = TILE + K + 1;                     // raw elements [tile0, tile0 + span) feed a tile
-    const int rspan = gae_pipe_rspan(TILE, K);
-    float* raw = reinterpret_cast<float*>(gae_sm4);    // [GAE_STAGES][3][rspan]   dones | values | rewards
-    float2* pairs = reinterpret_cast<float2*>(raw + GAE_STAGES * 3 * rspan);   // [padc(span)]  (delta, gamma*lambda*nnt) per element
-    const int tid = threadIdx.x;
-
-    auto issue = [&](int64_t tile, int stage) {
-        if (tile < tiles) {
-            const int64_t tile0 = tile * TILE;
-            const int avail = (int)((L - tile0 < span) ? (L - tile0) : span);
-            float* sd = raw + stage * 3 * rspan;
-            float* sv = sd + rspan;
-            float* sr = sv + rspan;
-            const int n4 = vec ? (avail >> 2) : 0;
-            for (int q = tid; q < n4; q += THREADS) {
-                gae_cp16(sd + 4 * q, dones + tile0 + 4 * q);
-                gae_cp16(sv + 4 * q, values + tile0 + 4 * q);
-                gae_cp16(sr + 4 * q, rewards + tile0 + 4 * q);
-            }
-            for (int i = 4 * n4 + tid; i < avail; i += THREADS) {
-                gae_cp4(sd + i, dones + tile0 + i);
-                gae_cp4(sv + i, values + tile0 + i);
-                gae_cp4(sr + i, rewards + tile0 + i);
-            }
-        }
-        asm volatile("cp.async.commit_group;" ::: "memory");          // one group per pipeline slot, empty past the last tile
+    float2* pairs = reinterpret_cast<float2*>(gae_sm4);          // [padp(span)]
+    constexpr int CHAINS = TILE / CH, PASSES = TILE / 4 / THREADS;
+    static_assert(CHAINS <= THREADS && PASSES >= 1 && TILE % (4 * THREADS) == 0, "tile geometry");
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int span = TILE + K + 1;
+    const int64_t tile0 = (int64_t)blockIdx.x * TILE;
+    const int avail = (int)((L - tile0 < span) ? (L - tile0) : span);
+    const int nelem = avail - 1;                       // elements i in [0, nelem) have a successor inside [0, avail): they get a pair
+    const float* gd = dones + tile0;
+    const float* gv = values + tile0;
+    const float* gr = rewards + tile0;
+    const int nq = vec ? (nelem >> 2) : 0;
+    auto pair_group = [&](int q, const float4& d, const float4& v, const float4& r, float dn, float vn, float rn) {
+        const float2 p0 = gae_pair(d.y, v.y, r.y, v.x, gamma, gl), p1 = gae_pair(d.z, v.z, r.z, v.y, gamma, gl);
+        const float2 p2 = gae_pair(d.w, v.w, r.w, v.z, gamma, gl), p3 = gae_pair(dn, vn, rn, v.w, gamma, gl);
+        float4* dst = reinterpret_cast<float4*>(pairs + padp<CH>(4 * q));
+        dst[0] = make_float4(p0.x, p0.y, p1.x, p1.y);
+        dst[1] = make_float4(p2.x, p2.y, p3.x, p3.y);
     };
-
-    int64_t tile = blockIdx.x;
+    // element 4q + 4: the first element of the neighbour lane's group when that lane holds one, else one scalar load
+    auto successor = [&](int q, bool ok, float mine, const float* g) {
+        float nx = __shfl_down_sync(FULL, mine, 1);
+        if (ok && (lane == 31 || q + 1 >= nq)) nx = __ldg(g + 4 * q + 4);
+        return nx;
+    };
+    {   // the tile proper: all loads of the thread's passes are in flight before the first pair is formed
+        float4 d[PASSES], v[PASSES], r[PASSES];
 #pragma unroll
-    for (int s = 0; s < GAE_STAGES - 1; ++s) issue(tile + (int64_t)s * gridDim.x, s);
-    for (int it = 0; tile < tiles; tile += gridDim.x, ++it) {
-        const int stage = it % GAE_STAGES;
-        // the stage refilled here was consumed by iteration it - 1, which every thread left through the barrier below
-        issue(tile + (int64_t)(GAE_STAGES - 1) * gridDim.x, (it + GAE_STAGES - 1) % GAE_STAGES);
-        asm volatile("cp.async.wait_group %0;" ::"n"(GAE_STAGES - 1) : "memory");
-        __syncthreads();                               // this tile's raw arrays are visible; the previous tile's chains are done with pairs[]
-        const int64_t tile0 = tile * TILE;
-        const int avail = (int)((L - tile0 < span) ? (L - tile0) : span);
-        const float* sd = raw + stage * 3 * rspan;
-        const float* sv = sd + rspan;
-        const float* sr = sv + rspan;
-        for (int i = tid; i + 1 < avail; i += THREADS) {             // c_gae.pyx:24-27, the part that does not involve the carry
-            const float nnt = 1.0f - sd[i + 1];
-            const float delta = (sr[i + 1] + (gamma * sv[i + 1]) * nnt) - sv[i];
-            pairs[padc<CH>(i)] = make_float2(delta, gl * nnt);
+        for (int u = 0; u < PASSES; ++u) {
+            const int q = tid + u * THREADS;
+            d[u] = v[u] = r[u] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+            if (q < nq) {
+                d[u] = __ldg(reinterpret_cast<const float4*>(gd) + q);
+                v[u] = __ldg(reinterpret_cast<const float4*>(gv) + q);
+                r[u] = __ldg(reinterpret_cast<const float4*>(gr) + q);
+            }
         }
-        __syncthreads();
-        const int c0 = tid * CH;
-        const int64_t g0 = tile0 + c0;
-        if (g0 < L) {
-            int64_t hi = g0 + CH - 1 + K;              // warm-up start, clipped to L-2 (adv[L-1] = 0 starts the true scan)
-            if (hi > L - 2) hi = L - 2;
-            float last = 0.0f;
-            int i = (int)(hi - tile0);
-            // warm-up: groups of CH steps with the CH loads issued ahead of the dependent FMUL / FADD chain (an unclipped window starts
-            // on the last element of a padding group, so the CH offsets are compile-time constants)
-            for (; i - (CH - 1) >= c0 + CH && (i & (CH - 1)) == CH - 1; i -= CH) {
-                const float2* pp = pairs + padc<CH>(i - (CH - 1));
-                float2 p[CH];
 #pragma unroll
-                for (int u = 0; u < CH; ++u) p[u] = pp[u];
-#pragma unroll
-                for (int u = CH - 1; u >= 0; --u) last = p[u].x + p[u].y * last;               // c_gae.pyx:28
-            }
-            for (; i >= c0 + CH; --i) {
-                const float2 p = pairs[padc<CH>(i)];
-                last = p.x + p.y * last;
-            }
-            float o[CH];
-            {
-                const float2* pp = pairs + padc<CH>(c0);            // the chunk is one padding group: CH consecutive pairs
-                float2 p[CH];
-#pragma unroll
-                for (int k = 0; k < CH; ++k) p[k] = pp[k];          // (slots past L-2 hold stale values that are never used)
-#pragma unroll
-                for (int k = CH - 1; k >= 0; --k) {
-                    if (g0 + k <= L - 2) {
-                        last = p[k].x + p[k].y * last;
-                        o[k] = last;
-                    } else {
-                        o[k] = 0.0f;                   // adv[L-1]
-                    }
-                }
-            }
-            if (vec && g0 + CH <= L) {
-                float4* o4 = reinterpret_cast<float4*>(adv + g0);
-                o4[0] = make_float4(o[0], o[1], o[2], o[3]);
-                o4[1] = make_float4(o[4], o[5], o[6], o[7]);
-            } else {
-#pragma unroll
-                for (int k = 0; k < CH; ++k)
-                    if (g0 + k < L) adv[g0 + k] = o[k];
-            }
+        for (int u = 0; u < PASSES; ++u) {
+            const int q = tid + u * THREADS;
+            const bool ok = q < nq;
+            const float dn = successor(q, ok, d[u].x, gd), vn = successor(q, ok, v[u].x, gv), rn = successor(q, ok, r[u].x, gr);
+            if (ok) pair_group(q, d[u], v[u], r[u], dn, vn, rn);
         }
     }
-    asm volatile("cp.async.wait_all;" ::: "memory");
+    for (int q = tid + PASSES * THREADS; q - lane < nq; q += THREADS) {             // the warm-up halo behind the tile (whole warps)
+        const bool ok = q < nq;
+        float4 d = make_float4(0.0f, 0.0f, 0.0f, 0.0f), v = d, r = d;
+        if (ok) {
+            d = __ldg(reinterpret_cast<const float4*>(gd) + q);
+            v = __ldg(reinterpret_cast<const float4*>(gv) + q);
+            r = __ldg(reinterpret_cast<const float4*>(gr) + q);
+        }
+        const float dn = successor(q, ok, d.x, gd), vn = successor(q, ok, v.x, gv), rn = successor(q, ok, r.x, gr);
+        if (ok) pair_group(q, d, v, r, dn, vn, rn);
+    }
+    for (int i = 4 * nq + tid; i < nelem; i += THREADS)                              // ragged end / unaligned arrays
+        pairs[padp<CH>(i)] = gae_pair(__ldg(gd + i + 1), __ldg(gv + i + 1), __ldg(gr + i + 1), __ldg(gv + i), gamma, gl);
+    __syncthreads();
+    if (tid >= CHAINS) return;
+    const int c0 = tid * CH;
+    const int64_t g0 = tile0 + c0;
+    if (g0 >= L) return;
+    int64_t hi = g0 + CH - 1 + K;                      // warm-up start, clipped to L-2 (adv[L-1] = 0 starts the true scan)
+    if (hi > L - 2) hi = L - 2;
+    float last = 0.0f;
+    int i = (int)(hi - tile0);
+    // warm-up: whole groups of CH steps, loads ahead of the dependent FMUL / FADD chain (an unclipped window ends on a group's last element)
+#pragma unroll 2
+    for (; i - (CH - 1) >= c0 + CH && (i & (CH - 1)) == CH - 1; i -= CH) {
+        const float4* pp = reinterpret_cast<const float4*>(pairs + padp<CH>(i - (CH - 1)));
+        float4 p[CH / 2];
+#pragma unroll
+        for (int u = 0; u < CH / 2; ++u) p[u] = pp[u];
+#pragma unroll
+        for (int u = CH / 2 - 1; u >= 0; --u) {
+            last = p[u].z + p[u].w * last;             // c_gae.pyx:28
+            last = p[u].x + p[u].y * last;
+        }
+    }
+    for (; i >= c0 + CH; --i) {
+        const float2 p = pairs[padp<CH>(i)];
+        last = p.x + p.y * last;
+    }
+    float o[CH];
+    {
+        const float4* pp = reinterpret_cast<const float4*>(pairs + padp<CH>(c0));              // the chunk is one group
+        float4 p[CH / 2];
+#pragma unroll
+        for (int u = 0; u < CH / 2; ++u) p[u] = pp[u];                                         // (slots past L-2 hold stale values, unused)
+#pragma unroll
+        for (int u = CH / 2 - 1; u >= 0; --u) {
+            if (g0 + 2 * u + 1 <= L - 2) { last = p[u].z + p[u].w * last; o[2 * u + 1] = last; } else o[2 * u + 1] = 0.0f;   // adv[L-1] = 0
+            if (g0 + 2 * u <= L - 2) { last = p[u].x + p[u].y * last; o[2 * u] = last; } else o[2 * u] = 0.0f;
+        }
+    }
+    if (vec && g0 + CH <= L) {
+        float4* o4 = reinterpret_cast<float4*>(adv + g0);
+#pragma unroll
+        for (int u = 0; u < CH / 4; ++u) o4[u] = make_float4(o[4 * u], o[4 * u + 1], o[4 * u + 2], o[4 * u + 3]);
+    } else {
+#pragma unroll
+        for (int k = 0; k < CH; ++k)
+            if (g0 + k < L) adv[g0 + k] = o[k];
+    }
 }
 
 // one warp: coalesced staging of 1024-element chunks, lane 0 runs the recurrence.
@@ -280,22 +287,26 @@ extern "C" int phc_gae(const float* dones, const float* values, const float* rew
     }
     const int vec = aligned16(dones) && aligned16(values) && aligned16(rewards) && aligned16(advantages);
     if (K <= 64) {
-        // short window: the pipelined kernel.  2048-element tiles once there are two per SM, else 512-element tiles (more CTAs in
-        // flight for rollouts that do not fill the GPU); CTAs walk equal numbers of tiles.
-        const int sms = sm_count();
-        const bool big = (L + 2047) / 2048 >= 2 * (int64_t)sms;
-        const int tile = big ? 2048 : 512;
-        const size_t smem = gae_pipe_smem(tile, K);
-        const int64_t tiles = (L + tile - 1) / tile;
-        const int64_t resident = (int64_t)sms * (big ? 2 : 8);
-        const int64_t per = (tiles + resident - 1) / resident;
-        const unsigned grid = (unsigned)((tiles + per - 1) / per);
+        // short window: the direct kernel.  4096-element tiles (256 chains of 16) once the rollout fills the GPU, else 512-element
+        // tiles (64 chains of 8): more CTAs in flight
+#ifndef GAE_DCH
+#define GAE_DCH 16                                    // elements per chain thread of the big tiles (A/B: 8 -> 8.6 us, 16 -> 8.0 us, 32 -> 8.4 us)
+#endif
+        constexpr int BIG_TILE = 256 * GAE_DCH;
+        const bool big = (L + 2047) / 2048 >= 2 * (int64_t)sm_count();
+        const int tile = big ? BIG_TILE : 512;
+        const int ch = big ? GAE_DCH : 8;
+        const int span = tile + K + 1;
+        const size_t smem = (size_t)(span + 2 * (span / ch) + 4) * sizeof(float2);
+        const unsigned grid = (unsigned)((L + tile - 1) / tile);
         if (big) {
-            cudaError_t e = cudaFuncSetAttribute(gae_pipelined_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-            if (e != cudaSuccess) return fail((int)e, "%s: cudaFuncSetAttribute: %s", fn, cudaGetErrorString(e));
-            gae_pipelined_kernel<256><<<grid, 256, smem, s>>>(dones, values, rewards, L, gamma, gl, K, advantages, vec, tiles);
+            if (smem > 48 * 1024) {
+                cudaError_t e = cudaFuncSetAttribute(gae_direct_kernel<GAE_DCH, 256, BIG_TILE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+                if (e != cudaSuccess) return fail((int)e, "%s: cudaFuncSetAttribute: %s", fn, cudaGetErrorString(e));
+            }
+            gae_direct_kernel<GAE_DCH, 256, BIG_TILE><<<grid, 256, smem, s>>>(dones, values, rewards, L, gamma, gl, K, advantages, vec);
         } else {
-            gae_pipelined_kernel<64><<<grid, 64, smem, s>>>(dones, values, rewards, L, gamma, gl, K, advantages, vec, tiles);
+            gae_direct_kernel<8, 64, 512><<<grid, 64, smem, s>>>(dones, values, rewards, L, gamma, gl, K, advantages, vec);
         }
         return check_launch(fn);
     }
