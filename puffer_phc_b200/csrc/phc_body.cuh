@@ -47,41 +47,10 @@ PHC_HD BodyState blend_frames_t0(const BodyState& a, V3 off, SlerpPair sp) {
     return r;
 }
 
-// compute_imitation_observations_v6 for one body (common.py:137-173); b = simulated body, r = reference body.
-PHC_HD void task_obs_body(const BodyState& b, const BodyState& r, V3 root_pos, float hz, float hw, float* o_dpos,
-                          float* o_drot, float* o_dvel, float* o_dang, float* o_lpos, float* o_lrot) {
-    const Q4 hinv{0.0f, 0.0f, -hz, hw}, h{0.0f, 0.0f, hz, hw};
-    put3(o_dpos, rotate_z(-hz, hw, r.p - b.p));                               // :138-139
-    const Q4 dq = quat_mul(r.q, quat_conj(b.q));                              // :142-145
-    tan_norm(quat_mul(quat_mul(hinv, dq), h), o_drot);                        // :146-149, :169
-    put3(o_dvel, rotate_z(-hz, hw, r.v - b.v));                               // :152-153
-    put3(o_dang, rotate_z(-hz, hw, r.w - b.w));                               // :155-156
-    put3(o_lpos, rotate_z(-hz, hw, r.p - root_pos));                          // :159-162
-    tan_norm(quat_mul(hinv, r.q), o_lrot);                                    // :164-165
-}
-
-// compute_humanoid_observations_smpl_max for one body (common.py:57-89). o_pos is written for j >= 1 only.
-PHC_HD void self_obs_body(const BodyState& b, V3 root_pos, float hz, float hw, int j, float* o_pos, float* o_rot,
-                          float* o_vel, float* o_ang) {
-    const Q4 hinv{0.0f, 0.0f, -hz, hw};
-    if (j >= 1) put3(o_pos, rotate_z(-hz, hw, b.p - root_pos));               // :57-66
-    tan_norm(quat_mul(hinv, b.q), o_rot);                                     // :68-75
-    put3(o_vel, rotate_z(-hz, hw, b.v));                                      // :81-83
-    put3(o_ang, rotate_z(-hz, hw, b.w));                                      // :85-89
-}
-
-// The same self observation split in two so that the fused step can balance its two warp roles.
-PHC_HD void self_obs_pos_rot(const BodyState& b, V3 root_pos, float hz, float hw, int j, float* o_pos, float* o_rot) {
-    const Q4 hinv{0.0f, 0.0f, -hz, hw};
-    if (j >= 1) put3(o_pos, rotate_z(-hz, hw, b.p - root_pos));               // :57-66
-    tan_norm(quat_mul(hinv, b.q), o_rot);                                     // :68-75
-}
-PHC_HD void self_obs_vel_ang(const BodyState& b, float hz, float hw, float* o_vel, float* o_ang) {
-    put3(o_vel, rotate_z(-hz, hw, b.v));                                      // :81-83
-    put3(o_ang, rotate_z(-hz, hw, b.w));                                      // :85-89
-}
-
-// Fused-step flavours (explicit fmaf chains, see phc_math.cuh): same outputs to a few ulp.
+// compute_imitation_observations_v6 (common.py:137-173) and compute_humanoid_observations_smpl_max (common.py:57-89) for one body;
+// b = simulated body, r = reference body, h = heading rotation of the simulated root.  Explicit fmaf chains (see phc_math.cuh): a few ulp
+// from the reference's op order.  Every kernel that produces observation rows (stand-alone, fused step, auto-reset tail) uses these,
+// and tests/host_math_harness.cpp replays them on the host against the reference's golden vectors.
 PHC_HD void task_obs_body_fma(const BodyState& b, const BodyState& r, V3 root_pos, float hz, float hw, const ZRot& h, float* o_dpos,
                               float* o_drot, float* o_dvel, float* o_dang, float* o_lpos, float* o_lrot) {
     put3(o_dpos, zrot_inv(h, r.p - b.p));                                                 // common.py:138-139
@@ -108,40 +77,13 @@ PHC_HD void reward_terms_body_fma(const BodyState& b, const BodyState& r, float&
     sa = fmaf(da.z, da.z, fmaf(da.y, da.y, da.x * da.x));
 }
 
-// compute_imitation_reward, per-body terms (common.py:298-316).
-PHC_HD void reward_terms_body(const BodyState& b, const BodyState& r, float& sp, float& sr, float& sv, float& sa) {
-    sp = mean_sq3(r.p - b.p);
-    const float ang = quat_angle(quat_mul(r.q, quat_conj(b.q)));
-    sr = ang * ang;
-    sv = mean_sq3(r.v - b.v);
-    sa = mean_sq3(r.w - b.w);
-}
-
-// Fused-step flavour of the per-body reward terms: plain sums of squares (the two means become one
-// multiplication per env) and the closed-form squared angle; <= a few ulp from reward_terms_body.
-PHC_HD void reward_terms_body_fast(const BodyState& b, const BodyState& r, float& sp, float& sr, float& sv, float& sa) {
-    sp = sum_sq3(r.p - b.p);
-    sr = quat_angle_sq(quat_mul(r.q, quat_conj(b.q)));
-    sv = sum_sq3(r.v - b.v);
-    sa = sum_sq3(r.w - b.w);
-}
-
-// env-level tail for reward_terms_body_fast: sp/sv/sa are sums over J bodies x 3 components, sr over J bodies.
+// env-level tail (common.py:300-320) for sums of squares: sp/sv/sa are sums over J bodies x 3 components, sr over J bodies.
 PHC_HD float reward_from_sq_sums(float sp, float sr, float sv, float sa, float J, const float* k, const float* w, float* raw) {
     const float inv3j = 1.0f / (3.0f * J), invj = 1.0f / J;
     raw[0] = expf(-k[0] * (sp * inv3j));
     raw[1] = expf(-k[1] * (sr * invj));
     raw[2] = expf(-k[2] * (sv * inv3j));
     raw[3] = expf(-k[3] * (sa * inv3j));
-    return ((w[0] * raw[0] + w[1] * raw[1]) + w[2] * raw[2]) + w[3] * raw[3];
-}
-
-// compute_imitation_reward, env-level tail (common.py:300-320): means over J, exp kernels, weighted sum.
-PHC_HD float reward_from_sums(float sp, float sr, float sv, float sa, float J, const float* k, const float* w, float* raw) {
-    raw[0] = expf(-k[0] * (sp / J));
-    raw[1] = expf(-k[1] * (sr / J));
-    raw[2] = expf(-k[2] * (sv / J));
-    raw[3] = expf(-k[3] * (sa / J));
     return ((w[0] * raw[0] + w[1] * raw[1]) + w[2] * raw[2]) + w[3] * raw[3];
 }
 

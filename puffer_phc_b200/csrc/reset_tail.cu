@@ -30,6 +30,9 @@ namespace phc {
 constexpr int AR_BLOCK = 1024;       // envs per scan CTA
 constexpr int AR_THREADS = 256;      // 4 envs per thread
 constexpr int AR_TWARPS = 8;         // warps per tail CTA
+#ifndef AR_TCTAS
+#define AR_TCTAS 2                    // tail CTAs per SM (68 KB of shared memory each; 3 would fit but need 80 registers: spills, 73.6 vs 68.3 us)
+#endif
 constexpr int AR_MAX_BLOCKS = 4096;  // N <= 4 Mi envs per call
 constexpr int AR_ROW = 936;          // floats per row buffer (934 padded to a multiple of 4)
 constexpr int AR_COLS = (934 + 31) / 32;   // observation columns per lane
@@ -82,20 +85,42 @@ __global__ void __launch_bounds__(AR_THREADS) auto_reset_scan_kernel(const ARArg
 #pragma unroll
     for (int k = 0; k < AR_NM; ++k) m[k] = 0.0;
     unsigned flagged = 0;
+    // phase 1: every input of the thread's four envs is requested before anything is stored (the stores below may alias the loads as far
+    // as the compiler knows, so a single loop would pay one memory round trip per env: the kernel is pure latency, 64 CTAs at 65536 envs)
+    bool ok[4], rs[4], tm[4];
+    float rw[4], rt[4];
+    int32_t ln[4];
+    int64_t mid[4];
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
         const int64_t e = e0 + k;
-        if (e >= a.N) break;
-        const bool r = env.reset[e] != 0, t = env.terminated[e] != 0;
+        ok[k] = e < a.N;
+        rs[k] = tm[k] = false; rw[k] = rt[k] = 0.0f; ln[k] = 0; mid[k] = 0;
+        if (ok[k]) {
+            rs[k] = env.reset[e] != 0;
+            tm[k] = env.terminated[e] != 0;
+            rw[k] = bk.rewards ? bk.rewards[e] : 0.0f;
+            if (bk.episode_returns) {
+                rt[k] = bk.episode_returns[e];
+                ln[k] = bk.episode_lengths ? bk.episode_lengths[e] : 0;
+            }
+            mid[k] = __ldg(env.motion_ids + e);
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int64_t e = e0 + k;
+        if (!ok[k]) continue;
+        const bool r = rs[k], t = tm[k];
         const bool trunc = r && !t;                                        // env.py:128-129
         if (r) flagged |= 1u << k;
         if (bk.terminals) bk.terminals[e] = t ? 1 : 0;                     // env.py:124-126 (terminate is a subset of reset)
         if (bk.truncations) bk.truncations[e] = trunc ? 1 : 0;
         if (bk.masks) bk.masks[e] = trunc ? 0 : 1;                         // env.py:132-133
-        const float rew = bk.rewards ? bk.rewards[e] : 0.0f;
+        const float rew = rw[k];
         if (bk.episode_returns) {
-            float ret = bk.episode_returns[e];
-            int32_t len = bk.episode_lengths ? bk.episode_lengths[e] : 0;
+            float ret = rt[k];
+            int32_t len = ln[k];
             if (r) {                                                       // env.py:116-120
                 m[PHC_M_EP_RETURN - 1] += (double)ret;
                 m[PHC_M_EP_LENGTH - 1] += (double)len;
@@ -144,10 +169,10 @@ __global__ void __launch_bounds__(AR_THREADS) auto_reset_scan_kernel(const ARArg
     for (int k = 0; k < 4; ++k)
         if ((flagged >> k) & 1u) {
             const int64_t e = e0 + k;
-            const int64_t id = __ldg(env.motion_ids + e);
+            const int64_t id = mid[k];
             ARec rc;
             rc.e_local = tid * 4 + k;
-            rc.truncated = env.terminated[e] == 0;
+            rc.truncated = !tm[k];
             rc.id = id;
             rc.nf = __ldg(a.t.num_frames + id);
             rc.ls = __ldg(a.t.length_starts + id);
@@ -187,15 +212,16 @@ __device__ __forceinline__ BodyState blend_pair(const RawPair& a, float blend, V
     return r;
 }
 
-__global__ void __launch_bounds__(AR_TWARPS * 32) auto_reset_tail_kernel(const ARArgs a) {
+__global__ void __launch_bounds__(AR_TWARPS * 32, AR_TCTAS) auto_reset_tail_kernel(const ARArgs a) {
     extern __shared__ double smem_d[];
     const bool mom = a.moment_partials != nullptr;
-    double* acc = smem_d;                                                        // [AR_TWARPS][2][OBS_W] (only with moments)
-    float* rows = reinterpret_cast<float*>(smem_d + (mom ? AR_TWARPS * 2 * OBS_W : 0));   // [AR_TWARPS][AR_ROW]
-    float* s_mean = rows + AR_TWARPS * AR_ROW;                                   // [AR_ROW] RunningNorm mean (only with obs_norm)
+    float* rows = reinterpret_cast<float*>(smem_d);                              // [AR_TWARPS][AR_ROW] the new observation rows
+    float* olds = rows + AR_TWARPS * AR_ROW;                                     // [AR_TWARPS][AR_ROW] the rows they replace (only with moments)
+    float* s_mean = olds + (mom ? AR_TWARPS * AR_ROW : 0);                       // [AR_ROW] RunningNorm mean (only with obs_norm)
     float* s_inv = s_mean + AR_ROW;                                              // [AR_ROW] 1 / sqrt(var + eps), one IEEE sqrt + division per column per CTA
     int* prefix = reinterpret_cast<int*>(s_inv + AR_ROW);                        // [nb + 1] exclusive prefix of the block counts
     __shared__ int s_part[AR_TWARPS * 32];
+    __shared__ int s_flag[AR_TWARPS];             // this round's env of warp w: 0 none, 1 reset after a termination, 2 truncated
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const phc_motion_tables& T = a.t;
     const phc_reset_env& env = a.env;
@@ -209,8 +235,6 @@ __global__ void __launch_bounds__(AR_TWARPS * 32) auto_reset_tail_kernel(const A
         if (b < a.nb) local += a.block_counts[b];
     }
     s_part[tid] = local;
-    if (mom)
-        for (int i = tid; i < AR_TWARPS * 2 * OBS_W; i += AR_TWARPS * 32) acc[i] = 0.0;
     if (env.obs_norm)
         for (int c = tid; c < OBS_W; c += AR_TWARPS * 32) {
             s_mean[c] = __ldg(env.rms_mean + c);
@@ -247,10 +271,24 @@ __global__ void __launch_bounds__(AR_TWARPS * 32) auto_reset_tail_kernel(const A
     }
 
     float* row = rows + warp * AR_ROW;
-    double* wacc = acc + (size_t)warp * 2 * OBS_W;
+    float* old = olds + warp * AR_ROW;
+    // moment correction: thread t of the CTA owns columns t, t + 256, ... and adds the CTA's (up to) eight rows of a round in warp
+    // order -- fp64 accumulators in REGISTERS, a fixed order, and no per-warp accumulator arrays in shared memory (those had held
+    // the kernel at one CTA = 8 warps per SM; now three CTAs fit)
+    // (thread t owns the column PAIRS t and t + 256: 8-byte shared-memory loads)
+    constexpr int AR_TCOLS = 2 * ((OBS_W / 2 + AR_TWARPS * 32 - 1) / (AR_TWARPS * 32));
+    static_assert(OBS_W % 2 == 0 && AR_ROW % 2 == 0, "column pairs");
+    const bool vec2 = (reinterpret_cast<uintptr_t>(env.obs) & 7u) == 0 && (env.obs_stride & 1) == 0 &&
+                      (!env.obs_norm || (reinterpret_cast<uintptr_t>(env.obs_norm) & 7u) == 0);
+    double as[AR_TCOLS], aq[AR_TCOLS];
+#pragma unroll
+    for (int k = 0; k < AR_TCOLS; ++k) as[k] = aq[k] = 0.0;
     const int total_warps = gridDim.x * AR_TWARPS;
     const float fps = (float)(1.0 / 30.0);        // curr_fps = 1/30 as a Python double, cast at the op (motion_lib.py:532)
-    for (int r = blockIdx.x * AR_TWARPS + warp; r < K; r += total_warps) {
+    for (int r0 = blockIdx.x * AR_TWARPS; r0 < K; r0 += total_warps) {
+      const int r = r0 + warp;
+      if (mom && lane == 0) s_flag[warp] = 0;
+      if (r < K) {
         int lo = 0, hi = a.nb;                     // largest block with prefix <= r
         while (hi - lo > 1) {
             const int mid = (lo + hi) >> 1;
@@ -264,11 +302,16 @@ __global__ void __launch_bounds__(AR_TWARPS * 32) auto_reset_tail_kernel(const A
         float* nrow = env.obs_norm ? env.obs_norm + e * env.obs_stride : nullptr;
         // the pre-reset observation row (only needed for the moment correction): all 30 loads per lane are issued here, before the two
         // motion-state queries, so that their latency hides behind the gathers and the math instead of following them
-        float ov[AR_COLS];
-#pragma unroll
-        for (int k = 0; k < AR_COLS; ++k) {
-            const int c = lane + 32 * k;
-            ov[k] = (mom && c < OBS_W) ? orow[c] : 0.0f;
+        if (mom) {                                             // 934 floats = 467 8-byte pieces (rows are 8-byte aligned when the
+            if ((reinterpret_cast<uintptr_t>(orow) & 7u) == 0) {   // stride is even), asynchronously: no registers, no stall here
+                for (int i = lane; i < OBS_W / 2; i += 32)
+                    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((unsigned)__cvta_generic_to_shared(old + 2 * i)), "l"(orow + 2 * i) : "memory");
+            } else {
+                for (int i = lane; i < OBS_W; i += 32)
+                    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((unsigned)__cvta_generic_to_shared(old + i)), "l"(orow + i) : "memory");
+            }
+            asm volatile("cp.async.commit_group;" ::: "memory");
+            if (lane == 0) s_flag[warp] = truncated ? 2 : 1;
         }
         const float mlen = rc.mlen, mdt = rc.mdt;
         const int64_t nf = rc.nf, ls = rc.ls;
@@ -342,35 +385,75 @@ __global__ void __launch_bounds__(AR_TWARPS * 32) auto_reset_tail_kernel(const A
             task_obs_body_fma(b, ref, root_p, hz, hw, hrot, q + 3 * j, q + 72 + 6 * j, q + 216 + 3 * j, q + 288 + 3 * j, q + 360 + 3 * j,
                               q + 432 + 6 * j);
         }
+        // the asynchronous copy of the pre-reset row must have READ the global row before the loop below overwrites it
+        if (mom) asm volatile("cp.async.wait_all;" ::: "memory");
         __syncwarp();
+        if (vec2) {                                              // 8-byte aligned rows: column pairs
 #pragma unroll
-        for (int k = 0; k < AR_COLS; ++k) {
-            const int c = lane + 32 * k;
-            if (c < OBS_W) {
-                const float nv = row[c];
-                if (mom) {
-                    const double od = (double)ov[k], nd = (double)nv;
-                    if (truncated) { wacc[c] -= od; wacc[OBS_W + c] -= od * od; }
-                    else { wacc[c] += nd - od; wacc[OBS_W + c] += nd * nd - od * od; }
+            for (int k = 0; k < (OBS_W / 2 + 31) / 32; ++k) {
+                const int c = 2 * (lane + 32 * k);
+                if (c < OBS_W) {
+                    const float2 nv = *reinterpret_cast<const float2*>(row + c);
+                    *reinterpret_cast<float2*>(orow + c) = nv;
+                    if (nrow) {
+                        const float2 m = *reinterpret_cast<const float2*>(s_mean + c), iv = *reinterpret_cast<const float2*>(s_inv + c);
+                        float y0 = (nv.x - m.x) * iv.x, y1 = (nv.y - m.y) * iv.y;
+                        y0 = (y0 != y0) ? y0 : fminf(fmaxf(y0, -cfg.rms_clip), cfg.rms_clip);
+                        y1 = (y1 != y1) ? y1 : fminf(fmaxf(y1, -cfg.rms_clip), cfg.rms_clip);
+                        *reinterpret_cast<float2*>(nrow + c) = make_float2(y0, y1);
+                    }
                 }
-                orow[c] = nv;
-                if (nrow) {
-                    float y = (nv - s_mean[c]) * s_inv[c];
-                    y = (y != y) ? y : fminf(fmaxf(y, -cfg.rms_clip), cfg.rms_clip);
-                    nrow[c] = y;
+            }
+        } else {
+#pragma unroll
+            for (int k = 0; k < AR_COLS; ++k) {
+                const int c = lane + 32 * k;
+                if (c < OBS_W) {
+                    const float nv = row[c];
+                    orow[c] = nv;
+                    if (nrow) {
+                        float y = (nv - s_mean[c]) * s_inv[c];
+                        y = (y != y) ? y : fminf(fmaxf(y, -cfg.rms_clip), cfg.rms_clip);
+                        nrow[c] = y;
+                    }
                 }
             }
         }
         __syncwarp();
+      }
+      if (mom) {
+        __syncthreads();                                        // every warp's new row and (landed) old row are in shared memory
+        for (int w = 0; w < AR_TWARPS; ++w) {
+            const int f = s_flag[w];
+            if (f == 0) continue;
+            const float* nr = rows + w * AR_ROW;
+            const float* orr = olds + w * AR_ROW;
+#pragma unroll
+            for (int k = 0; k < AR_TCOLS / 2; ++k) {
+                const int c = 2 * (tid + k * AR_TWARPS * 32);
+                if (c < OBS_W) {
+                    const float2 o2 = *reinterpret_cast<const float2*>(orr + c), n2 = *reinterpret_cast<const float2*>(nr + c);
+                    const double od0 = (double)o2.x, od1 = (double)o2.y, nd0 = (double)n2.x, nd1 = (double)n2.y;
+                    if (f == 2) { as[2 * k] -= od0; aq[2 * k] -= od0 * od0; as[2 * k + 1] -= od1; aq[2 * k + 1] -= od1 * od1; }
+                    else {
+                        as[2 * k] += nd0 - od0; aq[2 * k] += nd0 * nd0 - od0 * od0;
+                        as[2 * k + 1] += nd1 - od1; aq[2 * k + 1] += nd1 * nd1 - od1 * od1;
+                    }
+                }
+            }
+        }
+        __syncthreads();                                        // the row buffers are free for the next round
+      }
     }
     if (mom) {
-        __syncthreads();
         double* slot = a.moment_partials + (int64_t)blockIdx.x * 2 * OBS_W;
-        for (int c = tid; c < 2 * OBS_W; c += AR_TWARPS * 32) {
-            double s = acc[c];
 #pragma unroll
-            for (int w = 1; w < AR_TWARPS; ++w) s += acc[(size_t)w * 2 * OBS_W + c];
-            slot[c] += s;
+        for (int k = 0; k < AR_TCOLS / 2; ++k) {
+            const int c = 2 * (tid + k * AR_TWARPS * 32);
+            if (c < OBS_W) {
+                slot[c] += as[2 * k]; slot[c + 1] += as[2 * k + 1];
+                slot[OBS_W + c] += aq[2 * k]; slot[OBS_W + c + 1] += aq[2 * k + 1];
+            }
         }
     }
 }
@@ -434,7 +517,7 @@ __global__ void __launch_bounds__(256) stats_reduce_kernel(double* __restrict__ 
 
 using namespace phc;
 
-extern "C" int phc_auto_reset_num_partials(void) { return sm_count(); }
+extern "C" int phc_auto_reset_num_partials(void) { return AR_TCTAS * sm_count(); }
 
 extern "C" int64_t phc_auto_reset_scratch_bytes(int64_t N) {
     if (N <= 0) return 0;
@@ -474,8 +557,7 @@ extern "C" int phc_auto_reset(const phc_motion_tables* t, const phc_reset_env* e
     auto_reset_scan_kernel<<<nb, AR_THREADS, 0, s>>>(a);
     int rc = check_launch(fn);
     if (rc) return rc;
-    const size_t smem = (moment_partials ? (size_t)AR_TWARPS * 2 * OBS_W * sizeof(double) : 0) + (size_t)(AR_TWARPS + 2) * AR_ROW * sizeof(float) +
-                        (size_t)(nb + 1) * sizeof(int);
+    const size_t smem = (size_t)((moment_partials ? 2 : 1) * AR_TWARPS + 2) * AR_ROW * sizeof(float) + (size_t)(nb + 1) * sizeof(int);
     cudaError_t e = cudaFuncSetAttribute(auto_reset_tail_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return fail((int)e, "%s: cudaFuncSetAttribute(%zu B smem): %s", fn, smem, cudaGetErrorString(e));
     auto_reset_tail_kernel<<<phc_auto_reset_num_partials(), AR_TWARPS * 32, smem, s>>>(a);
