@@ -30,4 +30,17 @@ for chunks, hs in ((1, 1), (2, 1), (4, 1), (2, 2), (4, 2), (4, 3), (8, 2)):
     for i in range(16): fs.step_host(hin[i % 2], chunks=chunks, h2d_streams=hs)
     torch.cuda.synchronize()
     out[f"chunks{chunks}_h2d{hs}_ms"] = (time.perf_counter() - t0) / 16 * 1e3
+# two steps in flight (wait=False handles, double-buffered staging)
+for chunks, hs in ((1, 1), (2, 1), (4, 1), (1, 2), (2, 2), (4, 2)):
+    for i in range(3): fs.step_host(hin[i % 2], chunks=chunks, h2d_streams=hs)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    pending = None
+    for i in range(16):
+        h = fs.step_host(hin[i % 2], chunks=chunks, h2d_streams=hs, wait=False)
+        if pending is not None: pending.result()
+        pending = h
+    pending.result()
+    torch.cuda.synchronize()
+    out[f"inflight2_chunks{chunks}_h2d{hs}_ms"] = (time.perf_counter() - t0) / 16 * 1e3
 print(json.dumps(out))

@@ -52,6 +52,17 @@ class StepConfig:
         return dataclasses.replace(self, termination_distance=0.5, reset_bodies=EVAL_BODY_IDS, use_mean=True)
 
 
+class HostStepHandle:
+    """A step queued by ``FusedStep.step_host(..., wait=False)``: ``result()`` blocks until its results are in host memory."""
+
+    def __init__(self, out: Dict[str, torch.Tensor], done: "torch.cuda.Event"):
+        self._out, self._done = out, done
+
+    def result(self) -> Dict[str, torch.Tensor]:
+        self._done.synchronize()
+        return self._out
+
+
 class FusedStep:
     def __init__(self, motion_lib: MotionLibBase, num_envs: int, cfg: Optional[StepConfig] = None,
                  rms: Optional[RunningNorm] = None, normalize: bool = False, accumulate_moments: bool = False,
@@ -222,23 +233,31 @@ class FusedStep:
     # ---- host-buffer entry (end-to-end path): H2D of the per-env inputs, the kernel, D2H of reward / flags ------------
     _HOST_KEYS = ("body_state", "progress", "start_time", "start_offset", "motion_ids", "global_offset", "dof_force", "dof_vel")
 
-    def step_host(self, host: Dict[str, torch.Tensor], chunks: int = 4, h2d_streams: int = 1) -> Dict[str, torch.Tensor]:
+    def step_host(self, host: Dict[str, torch.Tensor], chunks: int = 4, h2d_streams: int = 1, wait: bool = True):
         """Same step with HOST (ideally pinned) input tensors, as a simulator living on the host would hand them over.
         Returns host tensors ``reward, reward_raw, reset, terminated`` (valid on return); the observation buffers stay on
         the device for the policy (``self.obs_buf`` / ``self.obs_norm``).
 
         The envs are processed in ``chunks`` ranges: the H2D copy of range c+1 (copy stream) runs under the kernel of range c
-        (compute stream) and the D2H of range c-1 (second copy stream), so only the PCIe transfer of the inputs is exposed."""
+        (compute stream) and the D2H of range c-1 (second copy stream), so only the PCIe transfer of the inputs is exposed.
+
+        ``wait=False`` queues the step and returns a ``HostStepHandle`` at once; ``handle.result()`` blocks until this step's
+        results have landed in host memory and returns them.  Staging buffers (device inputs, pinned results) are double-buffered,
+        so a caller that alternates two env groups -- submit group B, then read group A's results -- keeps the H2D copy of one
+        step running under the kernels and the result read-back of the other; at most TWO steps may be in flight (the third
+        submission reuses the first one's buffers: call ``result()`` on a handle before submitting the step after next)."""
         keys = [k for k in self._HOST_KEYS if k in host and (self.cfg.use_power_reward or not k.startswith("dof_"))]
         if not hasattr(self, "_dev_in"):
-            self._dev_in = {k: torch.empty(host[k].shape, dtype=host[k].dtype, device=self.device) for k in keys}
             from . import hostmem                    # result buffers pinned on the NUMA node this GPU hangs off
-            self._host_out = {"reward": hostmem.pinned_empty(self.N, torch.float32, self.device),
-                              "reward_raw": hostmem.pinned_empty((self.N, self.raw_dim), torch.float32, self.device),
-                              "reset": hostmem.pinned_empty(self.N, torch.bool, self.device),
-                              "terminated": hostmem.pinned_empty(self.N, torch.bool, self.device)}
+            self._dev_in = [{k: torch.empty(host[k].shape, dtype=host[k].dtype, device=self.device) for k in keys} for _ in range(2)]
+            self._host_out = [{"reward": hostmem.pinned_empty(self.N, torch.float32, self.device),
+                               "reward_raw": hostmem.pinned_empty((self.N, self.raw_dim), torch.float32, self.device),
+                               "reset": hostmem.pinned_empty(self.N, torch.bool, self.device),
+                               "terminated": hostmem.pinned_empty(self.N, torch.bool, self.device)} for _ in range(2)]
+            self._slot_read = [None, None]           # event: the kernels that read staging slot s have finished
+            self._host_seq = 0
             self.host_h2d_bytes = sum(host[k].numel() * host[k].element_size() for k in keys)
-            self.host_d2h_bytes = sum(v.numel() * v.element_size() for v in self._host_out.values())
+            self.host_d2h_bytes = sum(v.numel() * v.element_size() for v in self._host_out[0].values())
         for k in keys:
             if host[k].is_cuda:
                 raise RuntimeError("step_host expects host tensors; use __call__ for device-resident inputs")
@@ -246,15 +265,24 @@ class FusedStep:
             # several copy streams: the fixed set-up time of one DMA transfer hides under the payload of another
             self._h2d_streams = [torch.cuda.Stream(device=self.device) for _ in range(max(1, int(h2d_streams)))]
             self._d2h_stream = torch.cuda.Stream(device=self.device)
-        d, N = self._dev_in, self.N
+        slot = self._host_seq & 1
+        self._host_seq += 1
+        d, ho, N = self._dev_in[slot], self._host_out[slot], self.N
         chunks = max(1, min(int(chunks), N // 8)) if N >= 8 else 1
         per = -(-N // chunks)
         per += (-per) % 8
         main = torch.cuda.current_stream(self.device)
         hs = self._h2d_streams
-        for st in hs:
-            st.wait_stream(main)                        # earlier kernels may still read the staging buffers
-        self._d2h_stream.wait_stream(main)
+        # this slot's staging buffers were last read by the kernels of the step before last: the copies wait for THOSE kernels
+        # only (not for the previous step's, which use the other slot and may still be queued behind their own copies)
+        if self._slot_read[slot] is not None:
+            for st in hs:
+                st.wait_event(self._slot_read[slot])
+        else:
+            for st in hs:
+                st.wait_stream(main)                    # first use: earlier work on the compute stream may still own the memory
+        # the kernels below overwrite the device-side result buffers the previous step's read-back copies from
+        main.wait_stream(self._d2h_stream)
         small = [k for k in keys if host[k].numel() * host[k].element_size() < (4 << 20)]     # per-env scalars: one copy each,
         with torch.cuda.stream(hs[-1]):                                                         # not one per range
             for k in small:
@@ -271,11 +299,19 @@ class FusedStep:
                        d.get("dof_force"), d.get("dof_vel"), env_range=(lo, hi))
             self._d2h_stream.wait_stream(main)
             with torch.cuda.stream(self._d2h_stream):
-                for k, v in self._host_out.items():
+                for k, v in ho.items():
                     v[lo:hi].copy_(out[k], non_blocking=True)
-        self._d2h_stream.synchronize()
+        ev = torch.cuda.Event()
+        ev.record(main)
+        self._slot_read[slot] = ev
+        done = torch.cuda.Event()
+        done.record(self._d2h_stream)
+        handle = HostStepHandle(ho, done)
+        if not wait:
+            return handle
+        handle.result()
         main.synchronize()
-        return self._host_out
+        return ho
 
     # ---- CUDA-graph replay: at small batch sizes the step is launch-bound (4096 envs = a few microseconds of GPU work) ------
     def capture(self, body_state, progress_buf, motion_start_times, motion_start_times_offset, sampled_motion_ids, global_offset,

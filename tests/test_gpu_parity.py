@@ -492,6 +492,28 @@ def test_step_host_pipelined_equals_device_step(golden):
         m, m0 = npy(rms.moments_buffer()), npy(rms0.moments_buffer())
         assert m[0] == m0[0] == N
         np.testing.assert_allclose(m, m0, rtol=1e-13, atol=1e-12)
+    # two steps in flight (wait=False, double-buffered staging and result buffers): each handle returns its own step's results
+    host2 = {k: v.clone().pin_memory() for k, v in host.items()}
+    host2["progress"] = (host2["progress"] + 2).pin_memory()
+    dev2 = {k: v.to(DEV) for k, v in host2.items()}
+    want2 = {k: v.clone() for k, v in fs0(dev2["body_state"], dev2["progress"], dev2["start_time"], dev2["start_offset"], dev2["motion_ids"],
+                                          dev2["global_offset"], dev2["dof_force"], dev2["dof_vel"]).items()}
+    want1 = {k: v.clone() for k, v in fs0(dev["body_state"], dev["progress"], dev["start_time"], dev["start_offset"], dev["motion_ids"],
+                                          dev["global_offset"], dev["dof_force"], dev["dof_vel"]).items()}
+    fs = FusedStep(lib, N, StepConfig(), rms=RunningNorm(934).to(DEV), normalize=True, accumulate_moments=True)
+    pending, seen = None, 0
+    for i in range(6):
+        h = fs.step_host(host2 if i % 2 else host, chunks=3, wait=False)
+        if pending is not None:
+            got, w = pending[0].result(), (want2 if pending[1] else want1)
+            for k in ("reward", "reward_raw", "reset", "terminated"):
+                assert torch.equal(got[k], w[k].cpu()), ("in flight", i, k)
+            seen += 1
+        pending = (h, i % 2)
+    got = pending[0].result()
+    assert torch.equal(got["reward"], want2["reward"].cpu()) and seen == 5
+    torch.cuda.synchronize()
+    assert torch.equal(fs.obs_buf, want2["obs"])
     with pytest.raises(ValueError):
         fs0(dev["body_state"], dev["progress"], dev["start_time"], dev["start_offset"], dev["motion_ids"], dev["global_offset"],
             dev["dof_force"], dev["dof_vel"], env_range=(4, 16))
