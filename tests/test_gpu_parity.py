@@ -264,8 +264,8 @@ def test_gae_full_size_vs_oracle(gam, lam):
 
 
 @pytest.mark.parametrize("gam,lam", [(0.98, 0.2), (0.9, 0.5), (0.0, 0.5)])
-def test_gae_pipelined_many_tiles_ragged_and_unaligned(gam, lam):
-    """The short-window kernel where a CTA walks several tiles (65536 x 32), lengths that end inside a tile / a chunk / a 16-byte
+def test_gae_short_window_many_tiles_ragged_and_unaligned(gam, lam):
+    """The short-window kernel on the big-tile path (65536 x 32) and the small-tile path, lengths that end inside a tile / a chunk / a 16-byte
     group, and array slices that are not 16-byte aligned (4-byte staging, scalar stores): bit-exact against the serial scan."""
     from oracle import c_oracle as co
     from puffer_phc_b200 import c_gae, synth
@@ -377,6 +377,14 @@ def test_config2_amass_4096_envs(amass_lib):
     T, host = amass_lib
     lib = MotionLibSMPL.from_tables(T, device=DEV)
     _check_against_oracle(host, lib, 4096, 1, T)
+
+
+@pytest.mark.parametrize("n", [148 * 3 + 1, 148 * 5 + 3, 148 * 8 - 1, 148 * 12 + 5, 148 * 12 * 2 + 11])
+def test_balanced_blocks_all_widths(amass_lib, n):
+    """The launcher spreads small batches evenly over the CTAs' iterations (here: 4, 6, 8 envs per block in one iteration, 8 in two,
+    10 in three, each with a ragged last block): same flags and rows as the oracle whatever the block width."""
+    host, lib, T = amass_lib
+    _check_against_oracle(host, lib, n, 5, T)
 
 
 def test_config4_amass_65536_envs(amass_lib):
