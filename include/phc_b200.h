@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define PHC_B200_VERSION 120 /* 0.1.2 */
+#define PHC_B200_VERSION 121 /* 0.1.3 */
 
 enum {
     PHC_OK = 0,
@@ -477,6 +477,36 @@ int phc_rms_finalize(const double *moments, int C, float *running_mean, float *r
 /* ------------------------------------------------------------------------------------------- */
 int phc_gae(const float *dones, const float *values, const float *rewards, int64_t L, float gamma, float gae_lambda,
             float *advantages, int mode, phc_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------- */
+/* Device-resident rollout buffer around compute_gae: the reference's */
+/* Experience.store / sort_training_data (puffer_phc/clean_pufferl/structs.py:108-145) and the GAE */
+/* call site (clean_pufferl/core.py:213-259), which keep host numpy arrays in arrival order, sort  */
+/* batch_size (env_id, step) tuples in Python and copy four arrays between host and device.        */
+/* ------------------------------------------------------------------------------------------- */
+
+/* One env step of all N envs (env id = index) into row t of the [T, N] arrays: values_row .. mask_row are the row pointers
+ * (&values[t * N] ...); done / trunc are float32 (flags_are_float != 0) or bool / uint8 vectors (trunc may be NULL); mask is
+ * bool / uint8 (truncated envs are masked out, clean_pufferl/env.py:133).  Also written: subrank_row[e] = non-masked envs before e
+ * in e's 32-env group, group_counts_row[g] = non-masked envs of group g (ceil(N / 32) ints per row); *row_count += the row's
+ * non-masked envs (zero it when the rollout starts); *stored += the same (running total, structs.py:104-106). */
+int phc_rollout_store(const float *value, const float *reward, const void *done, const void *trunc, int flags_are_float,
+                      const uint8_t *mask, int64_t N, float *values_row, float *rewards_row, float *dones_row,
+                      float *truncateds_row, uint8_t *mask_row, uint8_t *subrank_row, int32_t *group_counts_row,
+                      int32_t *row_count, int64_t *stored, phc_stream_t stream);
+
+/* sort_training_data + the gathers in front of compute_gae, for the T rows stored so far: the rows the reference would have stored
+ * (per step the non-masked envs in env order, until batch_size rows) ordered by (env, step).  Outputs (capacity >= batch_size
+ * elements each): sorted_dones / sorted_values / sorted_rewards (what core.py:249 hands to compute_gae), idxs (the reference's
+ * arrival row numbers in sorted order, structs.py:133-145) and pos_em (e * T + t of every kept element: index into the env-major
+ * flattening of any [T, N] array).  meta (device int64[4]) = {first step that passes batch_size (T if none), rows that step still
+ * stores, rows kept in total, T}: read meta[2] to size the results.  scratch: phc_rollout_scratch_bytes(N, T) bytes, 8-byte aligned.
+ * Four launches, no host synchronisation. */
+int64_t phc_rollout_scratch_bytes(int64_t N, int T);
+int phc_rollout_sort(const float *dones, const float *values, const float *rewards, const uint8_t *mask, const uint8_t *subrank,
+                     const int32_t *group_counts, const int32_t *row_counts, int64_t N, int T, int64_t batch_size, void *scratch,
+                     int64_t *meta, float *sorted_dones, float *sorted_values, float *sorted_rewards, int64_t *idxs,
+                     int64_t *pos_em, phc_stream_t stream);
 
 #ifdef __cplusplus
 }

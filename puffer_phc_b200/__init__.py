@@ -26,4 +26,4 @@ def install_c_gae_shim() -> str:
     return d
 
 
-__version__ = "0.1.2"
+__version__ = "0.1.3"

@@ -22,9 +22,10 @@ EXPORTS = (
     "phc_step_num_partials", "phc_step_fused", "phc_rms_forward", "phc_rms_scratch_doubles", "phc_rms_moments",
     "phc_rms_reduce_partials", "phc_rms_finalize", "phc_auto_reset_num_partials", "phc_auto_reset_scratch_bytes", "phc_auto_reset",
     "phc_stats_reduce", "phc_stats_comm_bytes", "phc_stats_allreduce_finalize", "phc_gae", "phc_build_motion_tables", "phc_build_motion_aa", "phc_cast_f64_f32", "phc_mpjpe", "phc_frame_blend",
+    "phc_rollout_store", "phc_rollout_scratch_bytes", "phc_rollout_sort",
 )
 
-VERSION = 120
+VERSION = 121
 NUM_METRICS = 16
 METRIC_NAMES = ("steps", "reward", "r_pos", "r_rot", "r_vel", "r_ang_vel", "r_power", "resets", "terminations", "truncations",
                 "episode_return", "episode_length", "episodes")
@@ -150,6 +151,9 @@ def _declare(lib):
     lib.phc_cast_f64_f32.argtypes = [P, I64, P, P]
     lib.phc_mpjpe.argtypes = [View, View, I64, I, P, I, P]
     lib.phc_frame_blend.argtypes = [P, P, P, P, I64, P, P, P, P]
+    lib.phc_rollout_store.argtypes = [P, P, P, P, I, P, I64, P, P, P, P, P, P, P, P, P, P]
+    lib.phc_rollout_scratch_bytes.argtypes, lib.phc_rollout_scratch_bytes.restype = [I64, I], I64
+    lib.phc_rollout_sort.argtypes = [P, P, P, P, P, P, P, I64, I, I64, P, P, P, P, P, P, P, P]
     for name in EXPORTS:
         fn = getattr(lib, name)
         if fn.restype is C.c_int and name not in ("phc_version", "phc_step_num_partials", "phc_auto_reset_num_partials"):

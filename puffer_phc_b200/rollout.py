@@ -5,8 +5,10 @@ around ``c_gae.compute_gae``.
 The reference keeps values / rewards / dones in host numpy arrays in *arrival order* (per step: the rows of the
 non-masked envs, until ``batch_size`` rows are stored), sorts them by ``(env_id, step)`` with a Python ``sorted()`` over
 131072 tuples, runs GAE on the host and copies the advantages back.  Here everything stays in HBM in a fixed ``[T, N]``
-layout (+ mask); the reference's arrival indices and its sorted order are reproduced with two prefix sums, and the scan
-runs in ``phc_gae`` -- no host round trip, one sync per rollout (the size of the ragged result).
+layout (+ mask); ``store`` is one launch per env step (``phc_rollout_store``), the reference's arrival indices and its sorted
+order come out of ``phc_rollout_sort`` (four launches: prefix sums over 32-env group counts, per-env offsets, a warp-per-env
+compaction that writes the sorted arrays contiguously), and the scan runs in ``phc_gae`` -- no host round trip, one sync per
+rollout (the size of the ragged result).  CUDA only: there is no host implementation.
 
 Semantics kept from the reference (all verified against a literal Python replay in tests/test_rollout.py):
 * ``store`` keeps, per step, only rows with ``mask`` true (truncated envs are masked out, clean_pufferl/env.py:133) and
@@ -21,6 +23,7 @@ from typing import Optional
 
 import torch
 
+from . import _ffi
 from .c_gae import compute_gae_cuda
 
 
@@ -30,39 +33,66 @@ class RolloutBuffer:
         # masked rows make a rollout longer than batch_size / num_envs steps; leave room (grown on demand)
         self.T = int(max_steps) if max_steps is not None else 2 * (-(-self.batch_size // self.N)) + 2
         self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise RuntimeError("RolloutBuffer: the rollout kernels are CUDA only (no host implementation)")
+        self.lib = _ffi.load()
         f = dict(dtype=torch.float32, device=self.device)
+        self.groups = -(-self.N // 32)
         self.values = torch.zeros(self.T, self.N, **f)
         self.rewards = torch.zeros(self.T, self.N, **f)
         self.dones = torch.zeros(self.T, self.N, **f)
         self.truncateds = torch.zeros(self.T, self.N, **f)
         self.mask = torch.zeros(self.T, self.N, dtype=torch.bool, device=self.device)
+        self._subrank = torch.zeros(self.T, self.N, dtype=torch.uint8, device=self.device)          # non-masked envs before e in its 32-env group
+        self._group_counts = torch.zeros(self.T, self.groups, dtype=torch.int32, device=self.device)
+        self._row_counts = torch.zeros(self.T, dtype=torch.int32, device=self.device)
         self.obs = torch.zeros(self.T, self.N, obs_dim, **f) if obs_dim else None
         self.step = 0
-        self._stored = torch.zeros((), dtype=torch.int64, device=self.device)    # rows stored so far (device counter, no sync)
+        self._stored = torch.zeros(1, dtype=torch.int64, device=self.device)      # rows stored so far (device counter, no sync)
+        self._meta = torch.zeros(4, dtype=torch.int64, device=self.device)
+        cap = self.batch_size
+        self._sorted_buf = {k: torch.empty(cap, **f) for k in ("dones", "values", "rewards")}
+        self._idxs_buf = torch.empty(cap, dtype=torch.int64, device=self.device)
+        self._pos_buf = torch.empty(cap, dtype=torch.int64, device=self.device)
+        self._scratch = None
         self.idxs = None
 
     # ---- structs.py:108-131 -------------------------------------------------------------------------------
     def store(self, value, reward, done, trunc, mask, obs=None) -> None:
-        """One env step for all N envs (env_id = arange(N)); everything stays on the device, nothing syncs."""
+        """One env step for all N envs (env_id = arange(N)): ONE launch, everything stays on the device, nothing syncs."""
         t = self.step
         if t >= self.T:
             self._grow()
-        self.values[t].copy_(value)
-        self.rewards[t].copy_(reward)
-        self.dones[t].copy_(done)
-        self.truncateds[t].copy_(trunc)
-        self.mask[t].copy_(mask)
+        _ffi.require_cuda(value, reward, done, mask)
+        value, reward = (x.to(torch.float32).contiguous().view(-1) for x in (value, reward))
+        flags_float = done.dtype != torch.bool and done.dtype != torch.uint8
+        if flags_float:
+            done = done.to(torch.float32).contiguous().view(-1)
+            trunc = None if trunc is None else trunc.to(torch.float32).contiguous().view(-1)
+        else:
+            done = done.contiguous().view(-1)
+            trunc = None if trunc is None else trunc.to(done.dtype).contiguous().view(-1)
+        mask = mask.to(torch.bool).contiguous().view(-1)
+        if not (value.numel() == reward.numel() == done.numel() == mask.numel() == self.N and (trunc is None or trunc.numel() == self.N)):
+            raise ValueError("RolloutBuffer.store: every per-env vector must have num_envs elements")
+        with _ffi.on_device(self.device):
+            _ffi.check(self.lib.phc_rollout_store(_ffi.ptr(value), _ffi.ptr(reward), _ffi.ptr(done), _ffi.ptr(trunc), int(flags_float),
+                                                  _ffi.ptr(mask), self.N, _ffi.ptr(self.values[t]), _ffi.ptr(self.rewards[t]),
+                                                  _ffi.ptr(self.dones[t]), _ffi.ptr(self.truncateds[t]), _ffi.ptr(self.mask[t]),
+                                                  _ffi.ptr(self._subrank[t]), _ffi.ptr(self._group_counts[t]), _ffi.ptr(self._row_counts[t:]),
+                                                  _ffi.ptr(self._stored), _ffi.stream_ptr()), "RolloutBuffer.store")
         if self.obs is not None and obs is not None:
             self.obs[t].copy_(obs)
-        self._stored += mask.sum()
         self.step += 1
+        self.idxs = None
 
     def _grow(self) -> None:
-        for name in ("values", "rewards", "dones", "truncateds", "mask", "obs"):
+        for name in ("values", "rewards", "dones", "truncateds", "mask", "obs", "_subrank", "_group_counts", "_row_counts"):
             a = getattr(self, name)
             if a is not None:
                 setattr(self, name, torch.cat([a, torch.zeros_like(a)], 0))
         self.T *= 2
+        self._scratch = None
 
     @property
     def full(self) -> bool:                       # structs.py:104-106 (one device->host read)
@@ -70,16 +100,25 @@ class RolloutBuffer:
 
     # ---- structs.py:133-145 -------------------------------------------------------------------------------
     def sort_training_data(self) -> torch.Tensor:
-        """Arrival indices (the reference's row numbers) in (env_id, step) order, as a device int64 tensor."""
+        """Arrival indices (the reference's row numbers) in (env_id, step) order, as a device int64 tensor.  Also leaves dones /
+        values / rewards in that order for ``compute_advantages``."""
         T = self.step
-        m = self.mask[:T]
-        rank = torch.cumsum(m.reshape(-1).to(torch.int64), 0).reshape(T, self.N)      # arrival rank (1-based), step-major
-        keep = m & (rank <= self.batch_size)                                          # store() stops at batch_size rows
-        keep_em = keep.t().reshape(-1)                                                # env-major order = sorted by (env, step)
-        pos = torch.nonzero(keep_em).squeeze(-1)                                      # the one sync of the rollout
-        arrival = (rank - 1).t().reshape(-1)
-        self.idxs = arrival[pos]
-        self._pos_em = pos                                                            # positions in the env-major [N*T] flattening
+        if T == 0:
+            raise RuntimeError("RolloutBuffer.sort_training_data: nothing stored")
+        need = int(self.lib.phc_rollout_scratch_bytes(self.N, self.T))
+        if self._scratch is None or self._scratch.numel() * 8 < need:
+            self._scratch = torch.empty((need + 7) // 8, dtype=torch.int64, device=self.device)
+        sb = self._sorted_buf
+        with _ffi.on_device(self.device):
+            _ffi.check(self.lib.phc_rollout_sort(_ffi.ptr(self.dones), _ffi.ptr(self.values), _ffi.ptr(self.rewards), _ffi.ptr(self.mask),
+                                                 _ffi.ptr(self._subrank), _ffi.ptr(self._group_counts), _ffi.ptr(self._row_counts), self.N, T,
+                                                 self.batch_size, _ffi.ptr(self._scratch), _ffi.ptr(self._meta), _ffi.ptr(sb["dones"]),
+                                                 _ffi.ptr(sb["values"]), _ffi.ptr(sb["rewards"]), _ffi.ptr(self._idxs_buf),
+                                                 _ffi.ptr(self._pos_buf), _ffi.stream_ptr()), "RolloutBuffer.sort_training_data")
+        rows = int(self._meta[2])                                                     # the one sync of the rollout
+        self.idxs = self._idxs_buf[:rows]
+        self._pos_em = self._pos_buf[:rows]                                           # positions in the env-major [N*T] flattening
+        self._rows = rows
         return self.idxs
 
     def _sorted(self, a: torch.Tensor) -> torch.Tensor:
@@ -90,7 +129,8 @@ class RolloutBuffer:
         """Advantages and returns in the reference's sorted order (length = number of stored rows)."""
         if self.idxs is None:
             self.sort_training_data()
-        d, v, r = self._sorted(self.dones), self._sorted(self.values), self._sorted(self.rewards)
+        n = self._rows
+        d, v, r = (self._sorted_buf[k][:n] for k in ("dones", "values", "rewards"))
         if extra_reward is not None:
             r = r + extra_reward.reshape(-1)                                          # adversarial reward, core.py:249
         adv = compute_gae_cuda(d, v, r, gamma, gae_lambda)
@@ -106,5 +146,5 @@ class RolloutBuffer:
     def reset(self) -> None:
         self.step = 0
         self._stored.zero_()
-        self.mask.zero_()
+        self._row_counts.zero_()
         self.idxs = None

@@ -29,7 +29,7 @@ def test_library_exports_every_declared_symbol():
     out = subprocess.check_output(["nm", "-D", "--defined-only", _ffi.library_path()], text=True)
     exported = set(re.findall(r"\bT (phc_[a-z0-9_]+)", out))
     assert set(declared) <= exported
-    assert lib.phc_version() == 120
+    assert lib.phc_version() == 121
 
 
 def test_library_contains_sm100a_code():

@@ -30,25 +30,50 @@ def make_case(N, T, batch, p_mask, seed):
             (g.random((T, N)) < 0.05).astype(np.float32), g.random((T, N)) >= p_mask, batch)
 
 
-CASES = [(16, 12, 128, 0.1, 0), (64, 40, 2048, 0.02, 1), (7, 9, 40, 0.3, 2), (32, 8, 256, 0.0, 3)]
-
-
-@pytest.mark.parametrize("N,T,batch,p_mask,seed", CASES)
-def test_sorted_arrival_indices_match_reference(N, T, batch, p_mask, seed):
-    v, r, d, m, B = make_case(N, T, batch, p_mask, seed)
-    rv, rr, rd, idxs = reference_replay(v, r, d, m, B)
-    buf = RolloutBuffer(N, B, device="cpu")
-    for t in range(T):
-        buf.store(torch.from_numpy(v[t]), torch.from_numpy(r[t]), torch.from_numpy(d[t]), torch.zeros(N), torch.from_numpy(m[t]))
-    got = buf.sort_training_data().numpy()
-    assert_equal(got, idxs, "sorted arrival indices")
-    assert_equal(buf._sorted(buf.values).numpy(), rv[idxs], "values in sorted order")
-    assert_equal(buf._sorted(buf.dones).numpy(), rd[idxs], "dones in sorted order")
-    assert buf.full == (m.sum() >= B)
+CASES = [(16, 12, 128, 0.1, 0), (64, 40, 2048, 0.02, 1), (7, 9, 40, 0.3, 2), (32, 8, 256, 0.0, 3), (1, 5, 3, 0.2, 5), (33, 3, 99, 0.0, 6),
+         (1500, 6, 7001, 0.15, 7), (1024, 3, 10 ** 6, 0.5, 8)]
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("N,T,batch,p_mask,seed", CASES + [(4096, 34, 131072, 0.01, 4)])
+@pytest.mark.parametrize("N,T,batch,p_mask,seed", CASES + [(40000, 4, 123457, 0.03, 9)])
+def test_sorted_arrival_indices_match_reference(N, T, batch, p_mask, seed):
+    """phc_rollout_store + phc_rollout_sort against the literal replay: arrival indices in (env, step) order, the sorted arrays, the
+    running row count; batch_size cutting a step in half, N not a multiple of 32 / 1024, more than 1024 env groups, nothing cut."""
+    v, r, d, m, B = make_case(N, T, batch, p_mask, seed)
+    rv, rr, rd, idxs = reference_replay(v, r, d, m, B)
+    dev = "cuda:0"
+    buf = RolloutBuffer(N, B, max_steps=2, device=dev)                 # grows on demand
+    for t in range(T):
+        if t % 2:       # bool flags straight from the env adapter ...
+            buf.store(torch.from_numpy(v[t]).to(dev), torch.from_numpy(r[t]).to(dev), torch.from_numpy(d[t] != 0).to(dev),
+                      torch.zeros(N, dtype=torch.bool, device=dev), torch.from_numpy(m[t]).to(dev))
+        else:           # ... or float vectors
+            buf.store(torch.from_numpy(v[t]).to(dev), torch.from_numpy(r[t]).to(dev), torch.from_numpy(d[t]).to(dev), None,
+                      torch.from_numpy(m[t]).to(dev))
+    got = buf.sort_training_data().cpu().numpy()
+    assert_equal(got, idxs, "sorted arrival indices")
+    assert_equal(buf._sorted(buf.values).cpu().numpy(), rv[idxs], "values in sorted order (generic gather)")
+    assert_equal(buf._sorted_buf["values"][: len(idxs)].cpu().numpy(), rv[idxs], "values in sorted order")
+    assert_equal(buf._sorted_buf["dones"][: len(idxs)].cpu().numpy(), rd[idxs], "dones in sorted order")
+    assert_equal(buf._sorted_buf["rewards"][: len(idxs)].cpu().numpy(), rr[idxs], "rewards in sorted order")
+    assert buf.full == (m.sum() >= B)
+    assert int(buf._stored) == int(m.sum())
+    # a second rollout in the same buffer
+    buf.reset()
+    for t in range(T - 1, -1, -1):
+        buf.store(torch.from_numpy(v[t]).to(dev), torch.from_numpy(r[t]).to(dev), torch.from_numpy(d[t]).to(dev), None, torch.from_numpy(m[t]).to(dev))
+    rv2, rr2, rd2, idxs2 = reference_replay(v[::-1], r[::-1], d[::-1], m[::-1], B)
+    assert_equal(buf.sort_training_data().cpu().numpy(), idxs2, "second rollout")
+    assert_equal(buf._sorted_buf["rewards"][: len(idxs2)].cpu().numpy(), rr2[idxs2], "second rollout rewards")
+
+
+def test_rollout_buffer_is_cuda_only():
+    with pytest.raises(RuntimeError):
+        RolloutBuffer(8, 16, device="cpu")
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("N,T,batch,p_mask,seed", CASES[:4] + [(4096, 34, 131072, 0.01, 4)])
 def test_advantages_match_reference_flat_gae(N, T, batch, p_mask, seed):
     from oracle import c_oracle as co
     v, r, d, m, B = make_case(N, T, batch, p_mask, seed)
