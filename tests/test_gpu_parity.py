@@ -383,7 +383,9 @@ def test_config2_amass_4096_envs(amass_lib):
 def test_balanced_blocks_all_widths(amass_lib, n):
     """The launcher spreads small batches evenly over the CTAs' iterations (here: 4, 6, 8 envs per block in one iteration, 8 in two,
     10 in three, each with a ragged last block): same flags and rows as the oracle whatever the block width."""
-    host, lib, T = amass_lib
+    from puffer_phc_b200.motion_lib import MotionLibSMPL
+    T, host = amass_lib
+    lib = MotionLibSMPL.from_tables(T, device=DEV)
     _check_against_oracle(host, lib, n, 5, T)
 
 
