@@ -55,6 +55,8 @@ class RolloutBuffer:
         self._idxs_buf = torch.empty(cap, dtype=torch.int64, device=self.device)
         self._pos_buf = torch.empty(cap, dtype=torch.int64, device=self.device)
         self._scratch = None
+        self._base = None
+        self._stored_ptr = _ffi.ptr(self._stored)
         self.idxs = None
 
     # ---- structs.py:108-131 -------------------------------------------------------------------------------
@@ -63,24 +65,35 @@ class RolloutBuffer:
         t = self.step
         if t >= self.T:
             self._grow()
-        _ffi.require_cuda(value, reward, done, mask)
-        value, reward = (x.to(torch.float32).contiguous().view(-1) for x in (value, reward))
-        flags_float = done.dtype != torch.bool and done.dtype != torch.uint8
-        if flags_float:
-            done = done.to(torch.float32).contiguous().view(-1)
-            trunc = None if trunc is None else trunc.to(torch.float32).contiguous().view(-1)
-        else:
-            done = done.contiguous().view(-1)
-            trunc = None if trunc is None else trunc.to(done.dtype).contiguous().view(-1)
-        mask = mask.to(torch.bool).contiguous().view(-1)
-        if not (value.numel() == reward.numel() == done.numel() == mask.numel() == self.N and (trunc is None or trunc.numel() == self.N)):
-            raise ValueError("RolloutBuffer.store: every per-env vector must have num_envs elements")
+        f32, N = torch.float32, self.N
+
+        def vec(x, dt):                            # the usual case (right dtype, contiguous) costs two attribute reads
+            if not x.is_cuda:
+                raise RuntimeError("puffer_phc_b200: expected CUDA tensors -- the kernels are the only implementation "
+                                   f"(got a tensor on {x.device})")
+            if x.dtype is not dt or not x.is_contiguous():
+                x = x.to(dt).contiguous()
+            if x.numel() != N:
+                raise ValueError("RolloutBuffer.store: every per-env vector must have num_envs elements")
+            return x
+        value, reward = vec(value, f32), vec(reward, f32)
+        flags_float = done.dtype is not torch.bool and done.dtype is not torch.uint8
+        fdt = f32 if flags_float else done.dtype
+        done = vec(done, fdt)
+        trunc = None if trunc is None else vec(trunc, fdt)
+        mask = vec(mask, torch.bool)
+        if self._base is None:                     # row pointers are base + t * row bytes: no tensor slicing per call
+            self._base = tuple(x.data_ptr() for x in (self.values, self.rewards, self.dones, self.truncateds, self.mask, self._subrank,
+                                                      self._group_counts, self._row_counts))
+        bv, br, bd, bt, bm, bs, bg, bc = self._base
+        r4, r1 = 4 * t * N, t * N
+        P = _ffi.C.c_void_p
         with _ffi.on_device(self.device):
-            _ffi.check(self.lib.phc_rollout_store(_ffi.ptr(value), _ffi.ptr(reward), _ffi.ptr(done), _ffi.ptr(trunc), int(flags_float),
-                                                  _ffi.ptr(mask), self.N, _ffi.ptr(self.values[t]), _ffi.ptr(self.rewards[t]),
-                                                  _ffi.ptr(self.dones[t]), _ffi.ptr(self.truncateds[t]), _ffi.ptr(self.mask[t]),
-                                                  _ffi.ptr(self._subrank[t]), _ffi.ptr(self._group_counts[t]), _ffi.ptr(self._row_counts[t:]),
-                                                  _ffi.ptr(self._stored), _ffi.stream_ptr()), "RolloutBuffer.store")
+            _ffi.check(self.lib.phc_rollout_store(P(value.data_ptr()), P(reward.data_ptr()), P(done.data_ptr()),
+                                                  P(None if trunc is None else trunc.data_ptr()), int(flags_float), P(mask.data_ptr()), N,
+                                                  P(bv + r4), P(br + r4), P(bd + r4), P(bt + r4), P(bm + r1), P(bs + r1),
+                                                  P(bg + 4 * t * self.groups), P(bc + 4 * t), self._stored_ptr, _ffi.stream_ptr()),
+                       "RolloutBuffer.store")
         if self.obs is not None and obs is not None:
             self.obs[t].copy_(obs)
         self.step += 1
@@ -93,6 +106,7 @@ class RolloutBuffer:
                 setattr(self, name, torch.cat([a, torch.zeros_like(a)], 0))
         self.T *= 2
         self._scratch = None
+        self._base = None
 
     @property
     def full(self) -> bool:                       # structs.py:104-106 (one device->host read)
