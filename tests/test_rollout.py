@@ -35,7 +35,7 @@ CASES = [(16, 12, 128, 0.1, 0), (64, 40, 2048, 0.02, 1), (7, 9, 40, 0.3, 2), (32
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("N,T,batch,p_mask,seed", CASES + [(40000, 4, 123457, 0.03, 9)])
+@pytest.mark.parametrize("N,T,batch,p_mask,seed", CASES + [(40000, 4, 123457, 0.03, 9), (50, 150, 5000, 0.1, 10), (37, 70, 10 ** 6, 0.05, 11)])
 def test_sorted_arrival_indices_match_reference(N, T, batch, p_mask, seed):
     """phc_rollout_store + phc_rollout_sort against the literal replay: arrival indices in (env, step) order, the sorted arrays, the
     running row count; batch_size cutting a step in half, N not a multiple of 32 / 1024, more than 1024 env groups, nothing cut."""
