@@ -86,3 +86,53 @@ def test_advantages_match_reference_flat_gae(N, T, batch, p_mask, seed):
     assert_equal(adv.cpu().numpy().view(np.uint32), want.view(np.uint32), "advantages (bit-exact)")
     assert_equal(ret.cpu().numpy().view(np.uint32), (want + rv[idxs]).view(np.uint32), "returns")
     assert_equal(buf.idxs.cpu().numpy(), idxs, "idxs")
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("N,T,batch,p_mask", [(45, 5, 100, 0.2), (2050, 3, 5000, 0.0), (1024, 70, 80000, 0.1)])
+def test_rollout_kernels_stay_inside_their_buffers(N, T, batch, p_mask):
+    """compute-sanitizer is not available on the pool: call the two entry points directly on buffers with guard zones on both sides
+    (rows, group counts, sorted outputs, scratch) and check that no guard word changed."""
+    from puffer_phc_b200 import _ffi
+    lib = _ffi.load()
+    dev = torch.device("cuda:0")
+    g = torch.Generator().manual_seed(N + T)
+    G = 64                                              # guard elements on each side
+    groups = -(-N // 32)
+
+    def guarded(n, dtype, fill):
+        t = torch.full((n + 2 * G,), fill, dtype=dtype, device=dev)
+        return t, t[G:G + n]
+
+    bufs = {k: guarded(T * N, torch.float32, -7.0) for k in ("values", "rewards", "dones", "truncs")}
+    bufs["mask"] = guarded(T * N, torch.uint8, 77)
+    bufs["subrank"] = guarded(T * N, torch.uint8, 77)
+    bufs["gcounts"] = guarded(T * groups, torch.int32, -7)
+    bufs["rcounts"] = guarded(T, torch.int32, -7)
+    bufs["rcounts"][1].zero_()
+    stored = torch.zeros(1, dtype=torch.int64, device=dev)
+    masks = torch.rand(T, N, generator=g) >= p_mask
+    for t in range(T):
+        v, r = torch.randn(N, generator=g).to(dev), torch.rand(N, generator=g).to(dev)
+        d, m = (torch.rand(N, generator=g) < 0.1).to(dev), masks[t].to(dev)
+        row = lambda k, w=N: _ffi.C.c_void_p(bufs[k][1].data_ptr() + t * w * bufs[k][1].element_size())
+        _ffi.check(lib.phc_rollout_store(_ffi.ptr(v), _ffi.ptr(r), _ffi.ptr(d), None, 0, _ffi.ptr(m), N, row("values"), row("rewards"),
+                                         row("dones"), row("truncs"), row("mask"), row("subrank"), row("gcounts", groups), row("rcounts", 1),
+                                         _ffi.ptr(stored), _ffi.stream_ptr()), "store")
+    rows = min(batch, int(masks.sum()))
+    out = {k: guarded(rows, torch.float32, -7.0) for k in ("sd", "sv", "sr")}
+    out["idxs"] = guarded(rows, torch.int64, -7)
+    out["pos"] = guarded(rows, torch.int64, -7)
+    nbytes = int(lib.phc_rollout_scratch_bytes(N, T))
+    scratch = guarded((nbytes + 7) // 8, torch.int64, -7)
+    meta = torch.zeros(4, dtype=torch.int64, device=dev)
+    _ffi.check(lib.phc_rollout_sort(_ffi.ptr(bufs["dones"][1]), _ffi.ptr(bufs["values"][1]), _ffi.ptr(bufs["rewards"][1]), _ffi.ptr(bufs["mask"][1]),
+                                    _ffi.ptr(bufs["subrank"][1]), _ffi.ptr(bufs["gcounts"][1]), _ffi.ptr(bufs["rcounts"][1]), N, T, batch,
+                                    _ffi.ptr(scratch[1]), _ffi.ptr(meta), _ffi.ptr(out["sd"][1]), _ffi.ptr(out["sv"][1]), _ffi.ptr(out["sr"][1]),
+                                    _ffi.ptr(out["idxs"][1]), _ffi.ptr(out["pos"][1]), _ffi.stream_ptr()), "sort")
+    torch.cuda.synchronize()
+    assert int(meta[2]) == rows and int(stored) == int(masks.sum())
+    for name, (full, inner) in list(bufs.items()) + list(out.items()) + [("scratch", scratch)]:
+        fill = full[0].item()
+        assert bool((full[:G] == fill).all()) and bool((full[G + inner.numel():] == fill).all()), f"{name}: guard zone overwritten"
+    assert bool((out["idxs"][1] >= 0).all()) and bool((out["idxs"][1] < rows).all()) and out["idxs"][1].unique().numel() == rows
