@@ -108,6 +108,9 @@ constexpr int ST_WBUF_F = ST_AUX_OFF + ST_AUX_F;     // per (env, role): sim rec
 #ifndef ST_DIAG_DEV0
 #define ST_DIAG_DEV0 0
 #endif
+#ifndef ST_DIAG_NOTAIL
+#define ST_DIAG_NOTAIL 0                              // timing experiment only: role A skips its env-level tail (outputs are wrong)
+#endif
 #ifndef ST_DIAG_NOFULLWAIT
 #define ST_DIAG_NOFULLWAIT 0
 #endif
@@ -514,6 +517,11 @@ __global__ void __maxnreg__(ST_MAXREG) step_fused_kernel(const StepArgs a) {   /
                     for (int k = 1; k < 6; ++k) s = s + src[8 * k];
                     red2[(slot * 6 + v) * 4 + p4] = s;
                 }
+#if ST_DIAG_NOTAIL
+                if (false) {
+#else
+                {
+#endif
                 PROF_BEGIN
                 group_sync(bar_id);
                 PROF_END(3)
@@ -571,6 +579,7 @@ __global__ void __maxnreg__(ST_MAXREG) step_fused_kernel(const StepArgs a) {   /
                         mm[1] = make_float4(r2, r3, pr, rst ? 1.0f : 0.0f);
                         mm[2] = make_float4(fallen ? 1.0f : 0.0f, 0.0f, 0.0f, 0.0f);
                     }
+                }
                 }
             } else if (valid) {
                 // ============ role B: every observation block (task obs against the reference at t+1, self obs) ===========
