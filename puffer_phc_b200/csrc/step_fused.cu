@@ -132,6 +132,13 @@ constexpr int ST_WBUF_F = ST_AUX_OFF + ST_AUX_F;     // per (env, role): sim rec
 #endif
 constexpr unsigned SPIN_LIMIT = 1u << 22;            // a stuck mbarrier traps (after a few seconds) instead of hanging the GPU
 
+#ifndef ST_WARP_PERM
+#define ST_WARP_PERM ((6 * (ST_SLOTS / 4) + ST_WRITERS + 1) == 24)      // the table below is for the 24-warp configuration
+#endif
+#if ST_WARP_PERM
+// physical warp -> logical warp; logical 0..8 role A, 9..17 role B, 18..22 writers, 23 planner
+__constant__ unsigned char c_warp_perm[24] = {0, 1, 2, 7, 3, 4, 5, 8, 6, 9, 10, 11, 18, 12, 13, 14, 19, 15, 16, 17, 23, 20, 21, 22};
+#endif
 // -DST_PROFILE=1: lane 0 of every compute warp accumulates the clock cycles it spends in each wait of its loop
 // (0 cp.async landing + group barrier, 1 plan barrier, 2 tile-release barrier, 3 group barriers: buffers free + the two of the
 // reduction, 4 whole loop) into
@@ -380,7 +387,16 @@ __global__ void __maxnreg__(ST_MAXREG) step_fused_kernel(const StepArgs a) {   /
                                               // written and its plan can be recycled.  Role A writes no tile rows, so the writers do
                                               // NOT wait for it before shipping a tile (full[] counts role B only).
 
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tid = threadIdx.x, lane = tid & 31;
+    // logical warp (role assignment) of this physical warp.  Warp p issues from SM sub-partition p % 4; with the identity mapping
+    // every role-A group (the critical role) has a warp on sub-partition 0, which then carries 3 role-A + 2 role-B + 1 writer warps,
+    // the heaviest mix of the four.  ST_WARP_PERM deals the roles so that the sub-partition with three role-A warps gets the lightest
+    // companions (two writers and the planner) and the others 2 A + 3 B + 1 writer each.
+#if ST_WARP_PERM
+    const int warp = c_warp_perm[tid >> 5];
+#else
+    const int warp = tid >> 5;
+#endif
     const phc_step_in& in = a.in;
     const phc_step_cfg& cfg = a.cfg;
     const phc_step_out& out = a.out;
@@ -611,7 +627,7 @@ __global__ void __maxnreg__(ST_MAXREG) step_fused_kernel(const StepArgs a) {   /
         cp_async_wait_all();
     } else if (warp < ST_CWARPS + ST_WWARPS) {
         // ====================================== writer warps =======================================
-        const int wtid = tid - ST_CWARPS * 32;
+        const int wtid = (warp - ST_CWARPS) * 32 + lane;
         const bool do_norm = out.obs_norm != nullptr;
         const bool do_mom = out.moment_partials != nullptr;
         const bool do_met = !ST_DIAG_NOMETRICS && out.metric_partials != nullptr && wtid < 12;
