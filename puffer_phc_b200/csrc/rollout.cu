@@ -202,17 +202,32 @@ __global__ void __launch_bounds__(256) rollout_gather_kernel(const float* __rest
     for (int t0 = 0; t0 < tend; t0 += RO_TCH) {
         const int rows = tend - t0 < RO_TCH ? tend - t0 : RO_TCH;
         __syncthreads();                               // the previous chunk has been consumed
-        for (int tr = warp; tr < rows; tr += 8) {
-            const int t = t0 + tr;
+        {   // every load of the warp's (up to) eight rows is requested before the first shared-memory store: one memory round trip per
+            // chunk instead of one per row (the kernel is latency-bound: 2 048 short-lived CTAs)
             const int64_t e = e0 + lane;
             const bool ok = e < N;
-            const int64_t src = (int64_t)t * N + e;
-            t_d[tr][lane] = ok ? dones[src] : 0.0f;
-            t_v[tr][lane] = ok ? values[src] : 0.0f;
-            t_r[tr][lane] = ok ? rewards[src] : 0.0f;
-            t_m[tr][lane] = ok ? mask[src] : (uint8_t)0;
-            t_s[tr][lane] = ok ? subrank[src] : (uint8_t)0;
-            if (lane == 0) { t_pref[tr] = prefix[(int64_t)t * group_stride + g]; t_R[tr] = R[t]; }
+            float rd[RO_TCH / 8], rv[RO_TCH / 8], rr[RO_TCH / 8];
+            uint8_t rm[RO_TCH / 8], rs[RO_TCH / 8];
+            int32_t rp[RO_TCH / 8];
+            int64_t rR[RO_TCH / 8];
+#pragma unroll
+            for (int u = 0; u < RO_TCH / 8; ++u) {
+                const int tr = warp + 8 * u, t = t0 + tr;
+                rd[u] = rv[u] = rr[u] = 0.0f; rm[u] = rs[u] = 0; rp[u] = 0; rR[u] = 0;
+                if (tr < rows) {
+                    const int64_t src = (int64_t)t * N + e;
+                    if (ok) { rd[u] = dones[src]; rv[u] = values[src]; rr[u] = rewards[src]; rm[u] = mask[src]; rs[u] = subrank[src]; }
+                    if (lane == 0) { rp[u] = prefix[(int64_t)t * group_stride + g]; rR[u] = R[t]; }
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < RO_TCH / 8; ++u) {
+                const int tr = warp + 8 * u;
+                if (tr < rows) {
+                    t_d[tr][lane] = rd[u]; t_v[tr][lane] = rv[u]; t_r[tr][lane] = rr[u]; t_m[tr][lane] = rm[u]; t_s[tr][lane] = rs[u];
+                    if (lane == 0) { t_pref[tr] = rp[u]; t_R[tr] = rR[u]; }
+                }
+            }
         }
         __syncthreads();
 #pragma unroll
