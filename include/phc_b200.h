@@ -224,9 +224,10 @@ int phc_sample_time_interval(const float *phase, const float *motion_len, int64_
 /* puffer_phc/envs/common.py                                                                    */
 /* ------------------------------------------------------------------------------------------- */
 
-/* compute_imitation_observations_v6 (common.py:106-176).  obs: [N, obs_stride >= 24*J], six
- * body-major blocks [3J,6J,3J,3J,3J,6J].  time_steps must be 1 (the only value the reference
- * passes, humanoid_phc.py:1097) else PHC_EUNSUPPORTED. */
+/* compute_imitation_observations_v6 (common.py:106-176).  obs: [N, obs_stride >= 24*J*time_steps]: per future step six
+ * body-major blocks [3J,6J,3J,3J,3J,6J], the time_steps groups one after the other.  The ref_* views describe
+ * N * time_steps rows (row b * time_steps + s = future step s of env b, i.e. the reference's .view(B, time_steps, J, .));
+ * the reference itself only ever passes time_steps = 1 (humanoid_phc.py:1097). */
 int phc_imitation_obs_v6(phc_view root_pos /* [N,3] */, phc_view root_rot /* [N,4] */,
                          phc_view body_pos, phc_view body_rot, phc_view body_vel, phc_view body_ang_vel,
                          phc_view ref_body_pos, phc_view ref_body_rot, phc_view ref_body_vel, phc_view ref_body_ang_vel,

@@ -48,18 +48,23 @@ __device__ __forceinline__ BodyState body_from_record(const float* s, int j) {
 
 struct ObsArgs {
     KView root_pos, root_rot, pos, rot, vel, ang, rpos, rrot, rvel, rang;
-    int64_t N; int J; int upright; float* obs; int64_t obs_stride;
+    int64_t N; int J; int upright; float* obs; int64_t obs_stride; int ts;
 };
 
+// One warp per (env, future step): with time_steps > 1 the reference views its reference tensors as [B, time_steps, J, .] and
+// evaluates every future step against the SAME simulated bodies (common.py:137-173); row b of the output is the time_steps blocks of
+// 24 J values one after the other.
 template <bool AOS>
 __global__ void __launch_bounds__(IM_WARPS * 32) imitation_obs_kernel(const ObsArgs a) {
     __shared__ __align__(16) float s_rec[AOS ? IM_WARPS * IM_REC : 4];
     const int lane = threadIdx.x & 31;
-    const int64_t n = (int64_t)blockIdx.x * IM_WARPS + (threadIdx.x >> 5);
-    if (n >= a.N) return;
+    const int64_t nv = (int64_t)blockIdx.x * IM_WARPS + (threadIdx.x >> 5);      // (env, step) index: the reference tensors' row
+    if (nv >= a.N * a.ts) return;
+    const int64_t n = a.ts == 1 ? nv : nv / a.ts;                                // env: the simulated tensors' row
+    const int step = (int)(nv - n * a.ts);
     const float* rec = s_rec + (AOS ? (threadIdx.x >> 5) * IM_REC : 0);
     BodyState r{};                                   // reference loads first: they fly while the record is staged
-    if (lane < a.J) r = BodyState{ld3(at(a.rpos, n, lane)), ld4(at(a.rrot, n, lane)), ld3(at(a.rvel, n, lane)), ld3(at(a.rang, n, lane))};
+    if (lane < a.J) r = BodyState{ld3(at(a.rpos, nv, lane)), ld4(at(a.rrot, nv, lane)), ld3(at(a.rvel, nv, lane)), ld3(at(a.rang, nv, lane))};
     if (AOS) stage_record(a.pos.ptr + n * a.pos.stride_env, a.J * REC, const_cast<float*>(rec), lane);
     Q4 rr = ld4(a.root_rot.ptr + n * a.root_rot.stride_env);
     if (!a.upright) rr = remove_base_rot(rr);
@@ -70,7 +75,7 @@ __global__ void __launch_bounds__(IM_WARPS * 32) imitation_obs_kernel(const ObsA
     const int j = lane, J = a.J;
     const BodyState b = AOS ? body_from_record(rec, j)
                             : BodyState{ld3(at(a.pos, n, j)), ld4(at(a.rot, n, j)), ld3(at(a.vel, n, j)), ld3(at(a.ang, n, j))};
-    float* o = a.obs + n * a.obs_stride;
+    float* o = a.obs + n * a.obs_stride + (int64_t)step * 24 * J;
     task_obs_body_fma(b, r, rp, hz, hw, zrot_make(hz, hw), o + 3 * j, o + 3 * J + 6 * j, o + 9 * J + 3 * j, o + 12 * J + 3 * j,
                       o + 15 * J + 3 * j, o + 18 * J + 6 * j);
 }
@@ -272,17 +277,17 @@ extern "C" int phc_imitation_obs_v6(phc_view root_pos, phc_view root_rot, phc_vi
                                     int upright, float* obs, int64_t obs_stride, phc_stream_t stream) {
     const char* fn = "phc_imitation_obs_v6";
     PHC_REQUIRE(N >= 0, PHC_EINVAL, "%s: N < 0", fn);
-    PHC_REQUIRE(time_steps == 1, PHC_EUNSUPPORTED, "%s: time_steps=%d (only 1 is implemented; the reference never passes another value)", fn, time_steps);
+    PHC_REQUIRE(time_steps >= 1, PHC_EINVAL, "%s: time_steps=%d < 1", fn, time_steps);
     PHC_REQUIRE(J >= 1 && J <= 32, PHC_ESHAPE, "%s: J=%d outside [1,32]", fn, J);
     if (N == 0) return PHC_OK;
     CHECK_VIEW(fn, root_pos); CHECK_VIEW(fn, root_rot); CHECK_VIEW(fn, body_pos); CHECK_VIEW(fn, body_rot);
     CHECK_VIEW(fn, body_vel); CHECK_VIEW(fn, body_ang_vel); CHECK_VIEW(fn, ref_body_pos); CHECK_VIEW(fn, ref_body_rot);
     CHECK_VIEW(fn, ref_body_vel); CHECK_VIEW(fn, ref_body_ang_vel);
     PHC_REQUIRE(obs, PHC_EINVAL, "%s: obs is NULL", fn);
-    PHC_REQUIRE(obs_stride >= 24 * J, PHC_ESHAPE, "%s: obs_stride=%lld < 24*J", fn, (long long)obs_stride);
+    PHC_REQUIRE(obs_stride >= (int64_t)24 * J * time_steps, PHC_ESHAPE, "%s: obs_stride=%lld < 24*J*time_steps", fn, (long long)obs_stride);
     ObsArgs a{kv(root_pos), kv(root_rot), kv(body_pos), kv(body_rot), kv(body_vel), kv(body_ang_vel), kv(ref_body_pos), kv(ref_body_rot),
-              kv(ref_body_vel), kv(ref_body_ang_vel), N, J, upright, obs, obs_stride};
-    const unsigned grid = (unsigned)((N + IM_WARPS - 1) / IM_WARPS);
+              kv(ref_body_vel), kv(ref_body_ang_vel), N, J, upright, obs, obs_stride, time_steps};
+    const unsigned grid = (unsigned)((N * time_steps + IM_WARPS - 1) / IM_WARPS);
     if (is_aos_record(body_pos, body_rot, body_vel, body_ang_vel)) imitation_obs_kernel<true><<<grid, IM_WARPS * 32, 0, (cudaStream_t)stream>>>(a);
     else imitation_obs_kernel<false><<<grid, IM_WARPS * 32, 0, (cudaStream_t)stream>>>(a);
     return check_launch(fn);

@@ -24,15 +24,23 @@ def _prep(*ts):
 
 def compute_imitation_observations_v6(root_pos, root_rot, body_pos, body_rot, body_vel, body_ang_vel, ref_body_pos,
                                       ref_body_rot, ref_body_vel, ref_body_ang_vel, time_steps: int, upright: bool, out=None):
-    """reference envs/common.py:106-176 -> ``[B, J*24]`` (six body-major blocks 3J|6J|3J|3J|3J|6J).  ``out`` (optional, beyond the
-    reference's signature): a ``[B, >= J*24]`` float32 buffer with unit inner stride to write into instead of allocating."""
+    """reference envs/common.py:106-176 -> ``[B, time_steps*J*24]`` (per future step six body-major blocks 3J|6J|3J|3J|3J|6J).  With
+    ``time_steps > 1`` the four reference tensors hold ``B*time_steps*J`` bodies, viewed as ``[B, time_steps, J, .]`` like the reference
+    does.  ``out`` (optional, beyond the reference's signature): a ``[B, >= time_steps*J*24]`` float32 buffer with unit inner stride to
+    write into instead of allocating."""
     lib = _ffi.load()
+    time_steps = int(time_steps)
+    if time_steps < 1:
+        raise ValueError("compute_imitation_observations_v6: time_steps must be >= 1")
+    B, J = body_pos.shape[0], body_pos.shape[1]
+    if time_steps > 1:                      # [B, time_steps, J, k] / [B*time_steps, J, k] / any shape with that many elements -> rows
+        ref_body_pos, ref_body_vel, ref_body_ang_vel = (x.reshape(B * time_steps, J, 3) for x in (ref_body_pos, ref_body_vel, ref_body_ang_vel))
+        ref_body_rot = ref_body_rot.reshape(B * time_steps, J, 4)
     ts = _prep(root_pos, root_rot, body_pos, body_rot, body_vel, body_ang_vel, ref_body_pos, ref_body_rot, ref_body_vel,
                ref_body_ang_vel)
-    B, J = ts[2].shape[0], ts[2].shape[1]
-    obs = torch.empty((B, 24 * J), dtype=torch.float32, device=ts[2].device) if out is None else out
+    obs = torch.empty((B, 24 * J * time_steps), dtype=torch.float32, device=ts[2].device) if out is None else out
     with _ffi.on_device(obs.device):
-        _ffi.check(lib.phc_imitation_obs_v6(*[_ffi.view3(t) for t in ts], B, J, int(time_steps), int(bool(upright)),
+        _ffi.check(lib.phc_imitation_obs_v6(*[_ffi.view3(t) for t in ts], B, J, time_steps, int(bool(upright)),
                                             _ffi.ptr(obs), obs.stride(0), _ffi.stream_ptr()), "compute_imitation_observations_v6")
     return obs
 

@@ -69,7 +69,8 @@ def test_argument_validation_without_gpu():
     assert lib.phc_gae(None, None, None, 0, 0.9, 0.9, None, 0, None) == _ffi.PHC_OK          # empty input is a no-op
     assert lib.phc_gae(None, None, None, 8, 0.9, 0.9, None, 7, None) == _ffi.PHC_EINVAL
     v = _ffi.View(1, 0, 0)
-    assert lib.phc_imitation_obs_v6(*([v] * 10), 4, 24, 2, 1, C.c_void_p(1), 576, None) == _ffi.PHC_EUNSUPPORTED
+    assert lib.phc_imitation_obs_v6(*([v] * 10), 4, 24, 0, 1, C.c_void_p(1), 576, None) == _ffi.PHC_EINVAL          # time_steps < 1
+    assert lib.phc_imitation_obs_v6(*([v] * 10), 4, 24, 2, 1, C.c_void_p(1), 576, None) == _ffi.PHC_ESHAPE          # row too narrow for 2 steps
     assert lib.phc_imitation_obs_v6(*([v] * 10), 4, 40, 1, 1, C.c_void_p(1), 960, None) == _ffi.PHC_ESHAPE
     assert lib.phc_imitation_obs_v6(*([v] * 10), 0, 24, 1, 1, None, 576, None) == _ffi.PHC_OK
     assert lib.phc_rms_forward(None, 934, None, None, 1e-5, 10.0, 4, 934, None, 934, None) == _ffi.PHC_EINVAL

@@ -307,14 +307,51 @@ def test_sample_time_interval(golden):
     assert torch.equal(ids, torch.multinomial(lib._sampling_batch_prob, num_samples=1000, replacement=True))
 
 
+@pytest.mark.parametrize("upright", [True, False])
+def test_imitation_obs_future_steps(golden, upright):
+    """time_steps = 3 (common.py:106-176 with its .view(B, time_steps, J, .) of the reference tensors): every future step is the
+    single-step observation of the same simulated bodies against that step's reference -- checked against the C oracle step by step
+    and, when oracle/_ref is staged, against the reference's own function on torch-CUDA."""
+    from oracle import c_oracle as co
+    from puffer_phc_b200.envs import common
+    S = golden["synth_step"]
+    st = cu(S["in_body_state"])
+    bp, br, bv, ba = fields(st)
+    N, TS = bp.shape[0], 3
+    g = torch.Generator().manual_seed(3)
+    refs1 = [cu(S[f"t1_{k}"]) for k in ("rg_pos", "rb_rot", "body_vel", "body_ang_vel")]
+    # three different "future" references per env: the golden t+1 reference, and two perturbed copies (rotations stay unit)
+    steps = []
+    for s in range(TS):
+        p = refs1[0] + 0.05 * s * torch.randn(refs1[0].shape, generator=g).to(DEV)
+        q = refs1[1].roll(s, 0).contiguous()
+        v = refs1[2] * (1.0 + 0.1 * s)
+        w = refs1[3].roll(-s, 0).contiguous()
+        steps.append((p, q, v, w))
+    stacked = [torch.stack([steps[s][k] for s in range(TS)], 1).contiguous() for k in range(4)]          # [N, TS, J, k]
+    got = common.compute_imitation_observations_v6(bp[:, 0], br[:, 0], bp, br, bv, ba, *stacked, TS, upright)
+    assert got.shape == (N, TS * 24 * 24)
+    for s in range(TS):
+        want = co.imitation_obs_v6(npy(bp[:, 0]), npy(br[:, 0]), npy(bp), npy(br), npy(bv), npy(ba), *[npy(x) for x in steps[s]], 1, upright)
+        assert_close(npy(got[:, s * 576:(s + 1) * 576]), want, what=f"future step {s}", row_scale=True)
+        one = common.compute_imitation_observations_v6(bp[:, 0], br[:, 0], bp, br, bv, ba, *steps[s], 1, upright)
+        assert torch.equal(got[:, s * 576:(s + 1) * 576], one), "a future step differs from the single-step kernel on the same inputs"
+    from oracle import ref_runner as rr
+    if rr.available():
+        Rm = rr.boot()
+        ref = Rm.common.compute_imitation_observations_v6(bp[:, 0].contiguous(), br[:, 0].contiguous(), bp.contiguous(), br.contiguous(),
+                                                          bv.contiguous(), ba.contiguous(), *stacked, TS, upright)
+        assert_close(npy(got), npy(ref), what="vs the reference's own function, time_steps = 3", row_scale=True)
+
+
 def test_error_behaviour(golden):
     from puffer_phc_b200.envs import common
     from puffer_phc_b200 import c_gae
     S = golden["synth_step"]
     bp, br, bv, ba = fields(cu(S["in_body_state"]))
     r1 = [cu(S[f"t1_{k}"]) for k in ("rg_pos", "rb_rot", "body_vel", "body_ang_vel")]
-    with pytest.raises(NotImplementedError):
-        common.compute_imitation_observations_v6(bp[:, 0], br[:, 0], bp, br, bv, ba, *r1, 2, True)
+    with pytest.raises(ValueError):
+        common.compute_imitation_observations_v6(bp[:, 0], br[:, 0], bp, br, bv, ba, *r1, 0, True)
     with pytest.raises(RuntimeError):
         common.compute_imitation_observations_v6(bp[:, 0].cpu(), br[:, 0], bp, br, bv, ba, *r1, 1, True)
     with pytest.raises(ValueError):
